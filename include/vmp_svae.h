@@ -1,0 +1,181 @@
+/* vmp_svae.h — C-ABI of libvmp_svae.so: the B200 (sm_100a) implementation of the local VMP step +
+ * natural-gradient global update of emtiyaz/vmp-for-svae.
+ *
+ * The reference has no FFI of its own: its hot path is the Python function surface of
+ * models/svae.py, models/gmm.py, models/smm.py and distributions/{gaussian,niw,dirichlet,student_t}.py,
+ * executed by TensorFlow 1.3 library kernels.  Each entry point below names the reference
+ * function(s) (file:line) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer to caller-owned, contiguous, row-major memory; the library
+ *    never allocates device memory and keeps no global state;
+ *  - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on it, no hidden syncs;
+ *  - `_f32` entry points take float buffers, `_f64` entry points double buffers (the fp64 build of the
+ *    north-star tolerance clause); integer outputs are int32; ELBO / sufficient-statistic accumulators
+ *    are always double;
+ *  - return value: 0 ok; <0 invalid argument (VMP_E_*); >0 a cudaError_t from the launch;
+ *  - N points, K mixture components, D latent dimension (1..64), S samples per (point, component).
+ */
+#ifndef VMP_SVAE_H
+#define VMP_SVAE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VMP_OK            0
+#define VMP_E_BADARG     -1   /* null pointer / non-positive size */
+#define VMP_E_BADDIM     -2   /* D outside 1..VMP_MAX_D */
+#define VMP_E_BADMODE    -3
+
+#define VMP_MAX_D        64
+
+/* denominators of the ELBO regulariser */
+#define VMP_DEN_GAUSS     0   /* log N(x | E_theta)   : svae.compute_elbo      (svae.py:199-262) */
+#define VMP_DEN_STUDENT   1   /* log St(x | mu,Sigma,nu): svae.compute_elbo_smm (svae.py:265-322) */
+
+int vmp_version(void);
+
+/* Number of scalars in one per-component record (see DESIGN.md "data layout"). */
+int vmp_phi_record_len(int D);      /* P2[D*D] | mu2[D] | h2[D] | log_pi, logdetP2, 0, 0            */
+int vmp_theta_record_len(int D);    /* W[D*D]  | m[D]   | cden, nu, E log pi, logdet P               */
+int vmp_stats_len(int D);           /* per component: N_k, W_k, sum w x [D], sum w x x^T [D*D]       */
+
+/* ---- per-step prologues (K-sized) -------------------------------------------------------------------
+ * phi_gmm -> per-component records.  Replaces svae.unpack_recognition_gmm (svae.py:342-358):
+ * L = tril(L_raw) with softplus diagonal, P2 = L L^T, pi = softmax(pi_raw); additionally mu2 = P2^-1 eta1,
+ * logdet P2.  eta1_phi2[K,D], L_raw[K,D,D], pi_raw[K] -> rec[K, vmp_phi_record_len(D)].               */
+int vmp_phi_prepare_f32(int K, int D, const float* eta1_phi2, const float* L_raw, const float* pi_raw,
+                        float* rec, void* stream);
+int vmp_phi_prepare_f64(int K, int D, const double* eta1_phi2, const double* L_raw, const double* pi_raw,
+                        double* rec, void* stream);
+
+/* theta (Dirichlet+NIW natural parameters) -> records for the ELBO denominator.  Replaces
+ * niw.natural_to_standard + niw.expected_values + gaussian.standard_to_natural + dirichlet.expected_log_pi
+ * as called from svae.compute_elbo (svae.py:204-208; niw.py:8-17,33-43; gaussian.py:11-19; dirichlet.py:8-12).
+ * alpha[K], A[K,D,D], b[K,D], beta[K], v_hat[K] -> rec[K, vmp_theta_record_len(D)].                   */
+int vmp_theta_prepare_gauss_f32(int K, int D, const float* alpha, const float* A, const float* b,
+                                const float* beta, const float* v_hat, float* rec, void* stream);
+int vmp_theta_prepare_gauss_f64(int K, int D, const double* alpha, const double* A, const double* b,
+                                const double* beta, const double* v_hat, double* rec, void* stream);
+/* SMM variant: theta = (alpha_nat[K], mu[K,D], L_raw[K,D,D], dof[K]).  Replaces svae.unpack_smm
+ * (svae.py:361-373) + the per-component constants of student_t._logprob_full_scale (student_t.py:7-39). */
+int vmp_theta_prepare_student_f32(int K, int D, const float* alpha, const float* mu, const float* L_raw,
+                                  const float* dof, float* rec, void* stream);
+int vmp_theta_prepare_student_f64(int K, int D, const double* alpha, const double* mu, const double* L_raw,
+                                  const double* dof, double* rec, void* stream);
+
+/* ---- the fused local step ---------------------------------------------------------------------------
+ * Replaces svae.e_step (svae.py:14-47: compute_log_z_given_y 50-92, sample_x_per_comp 95-119),
+ * svae.subsample_x(...)[:,0,:] (122-151, 514) and the regulariser of svae.compute_elbo /
+ * compute_elbo_smm (234-260 / 294-320) incl. gaussian.log_probability_nat (gaussian.py:30-71),
+ * log_probability_nat_per_samp (74-105), student_t.log_probability_per_samp (student_t.py:59-61).
+ *
+ * in : eta1[N,D], eta2_diag[N,D] (<0)  encoder natural parameters
+ *      phi_rec, theta_rec               from the prologues; den_mode VMP_DEN_*
+ *      noise[N,K,D,S] or NULL           injected raw noise (svae.py:113-114 layout); NULL -> Philox(seed)
+ *      u[N] or NULL                     injected uniforms of the categorical draw; NULL -> Philox(seed)
+ *      x_in[N,K,S,D] or NULL            evaluate these samples instead of drawing (svae.compute_elbo called with
+ *                                       caller-supplied x_k_samps); eps is recovered as a + L^T (x - mu1)
+ * out: log_r[N,K]                       normalised log q(z|y)         (may not be NULL)
+ *      x_sample[N,D], z[N]              the selected sample x[n, z_n, 0] and z_n (either may be NULL)
+ *      x_k_samples[N,K,S,D] or NULL     all samples (only materialise at small sizes)
+ *      elbo_acc[4] (double, ACCUMULATED into; caller zeroes): sum r*mean_s(log num), sum r*mean_s(log den),
+ *                                       regulariser = mean_s sum r (num - den), number of non-PD pivots   */
+int vmp_svae_local_step_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
+                            const float* phi_rec, const float* theta_rec, int den_mode,
+                            const float* noise, const float* u, uint64_t seed, const float* x_in,
+                            float* log_r, float* x_sample, int32_t* z, float* x_k_samples,
+                            double* elbo_acc, void* stream);
+int vmp_svae_local_step_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
+                            const double* phi_rec, const double* theta_rec, int den_mode,
+                            const double* noise, const double* u, uint64_t seed, const double* x_in,
+                            double* log_r, double* x_sample, int32_t* z, double* x_k_samples,
+                            double* elbo_acc, void* stream);
+
+/* The noise the in-kernel generator uses for a given seed, written in the reference layout
+ * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N] (either may be NULL).        */
+int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, float* noise, float* u, void* stream);
+int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, double* noise, double* u, void* stream);
+
+/* ---- responsibility-weighted sufficient statistics --------------------------------------------------
+ * Replaces the reductions of gmm.m_step (gmm.py:25-46,201-227: update_Nk/xk/Sk) and smm.m_step
+ * (smm.py:25-50,167-196) in additive form: stats[k] += [sum r, sum w, sum w x, sum w x x^T], w = r (GMM) or
+ * r*u (SMM, u_nk != NULL).  x[N,D]; r[N,K] = responsibilities, or their logs when r_is_log != 0
+ * (the SVAE path feeds log_r straight in: experiments.py:258-259 does tf.exp).  stats[K, vmp_stats_len(D)]
+ * is double and ACCUMULATED into (zero it first; all-reduce it across ranks before the update).      */
+int vmp_suffstats_f32(int64_t N, int K, int D, const float* x, const float* r, int r_is_log,
+                      const float* u_nk, double* stats, void* stream);
+int vmp_suffstats_f64(int64_t N, int K, int D, const double* x, const double* r, int r_is_log,
+                      const double* u_nk, double* stats, void* stream);
+
+/* ---- natural-gradient (CVI) update ------------------------------------------------------------------
+ * Replaces svae.m_step (svae.py:154-176) + svae.update_gmm_params (376-403):
+ * theta* = prior + [N_k, sum r x x^T, sum r x, N_k, N_k + 1]; theta <- (1-rho) theta + rho theta*, in place.
+ * theta_star_* (optional, may be NULL) receive theta*.  With only_alpha != 0 only alpha is touched
+ * (svae.m_step_smm, svae.py:179-196).                                                                 */
+int vmp_ng_update_f32(int K, int D, const double* stats, double rho, int only_alpha,
+                      const float* p_alpha, const float* p_A, const float* p_b, const float* p_beta, const float* p_vhat,
+                      float* alpha, float* A, float* b, float* beta, float* v_hat,
+                      float* s_alpha, float* s_A, float* s_b, float* s_beta, float* s_vhat, void* stream);
+int vmp_ng_update_f64(int K, int D, const double* stats, double rho, int only_alpha,
+                      const double* p_alpha, const double* p_A, const double* p_b, const double* p_beta, const double* p_vhat,
+                      double* alpha, double* A, double* b, double* beta, double* v_hat,
+                      double* s_alpha, double* s_A, double* s_b, double* s_beta, double* s_vhat, void* stream);
+
+/* ---- standalone mixture VB-EM -----------------------------------------------------------------------
+ * M-step in standard parameters from accumulated statistics.  Replaces gmm.update_* (gmm.py:25-81) when
+ * is_smm == 0 (NaN guards of 36,46; v_k = v_0 + N_k + 1) and smm.update_* (smm.py:25-85) when is_smm != 0
+ * (1e-20 eps; v_k = v_0 + N_k).  Outputs alpha_k[K], beta_k[K], m_k[K,D], C_k[K,D,D], v_k[K], x_k[K,D], S_k[K,D,D]. */
+int vmp_mixture_mstep_f32(int K, int D, int is_smm, const double* stats,
+                          const float* alpha_0, const float* beta_0, const float* m_0, const float* C_0, const float* v_0,
+                          float* alpha_k, float* beta_k, float* m_k, float* C_k, float* v_k, float* x_k, float* S_k,
+                          void* stream);
+int vmp_mixture_mstep_f64(int K, int D, int is_smm, const double* stats,
+                          const double* alpha_0, const double* beta_0, const double* m_0, const double* C_0, const double* v_0,
+                          double* alpha_k, double* beta_k, double* m_k, double* C_k, double* v_k, double* x_k, double* S_k,
+                          void* stream);
+
+/* E-steps.  gmm.e_step / e_step_missing_data (gmm.py:154-198 with 84-151) when kappa_k == NULL;
+ * smm.e_step (smm.py:140-164 with 88-137) otherwise.  x[N,D], alpha_k[K], beta_k[K], m_k[K,D], P_k[K,D,D],
+ * v_k[K], missing_mask[N,D] (uint8, may be NULL; GMM only) -> r[N,K], u_out[N,K] (SMM only), pi[K] = exp(E log pi).
+ * work[K]: caller-provided scratch for the per-component constants.                                    */
+int vmp_mixture_estep_f32(int64_t N, int K, int D, const float* x, const float* alpha_k, const float* beta_k,
+                          const float* m_k, const float* P_k, const float* v_k, const float* kappa_k,
+                          const uint8_t* missing_mask, float* r, float* u_out, float* pi, float* work, void* stream);
+int vmp_mixture_estep_f64(int64_t N, int K, int D, const double* x, const double* alpha_k, const double* beta_k,
+                          const double* m_k, const double* P_k, const double* v_k, const double* kappa_k,
+                          const uint8_t* missing_mask, double* r, double* u_out, double* pi, double* work,
+                          void* stream);
+
+/* Batched SPD inverse + log-determinant of K matrices (tf.matrix_inverse at gmm.py:260 / smm.py:234,
+ * helpers/tf_utils.logdet 25-49).  in[K,D,D] -> inv[K,D,D] (may be NULL), logdet[K] (may be NULL).      */
+int vmp_spd_inverse_f32(int K, int D, const float* in, float* inv, float* logdet, void* stream);
+int vmp_spd_inverse_f64(int K, int D, const double* in, double* inv, double* logdet, void* stream);
+
+/* ---- ELBO terms outside the fused step --------------------------------------------------------------
+ * Decoder-side weighted reductions.  mode 0: vae.expected_diagonal_gaussian_loglike, weighted branch
+ * (vae.py:226-248): acc += sum_{n,k,s,d} w_nk [ (y-mean)^2/var + log(var+1e-8) ]; mode 1:
+ * vae.expected_bernoulli_loglike (vae.py:175-198): acc += sum_{n,k,s,d} w_nk [ -log(1+exp(-logit*y)) ].
+ * y[N,Dobs], means/out2[N,K,S,Dobs] (means may be NULL in mode 1), w[N,K]; acc is one double, accumulated. */
+int vmp_decoder_loglike_f32(int64_t N, int K, int S, int Dobs, int mode, const float* y, const float* means,
+                            const float* out2, const float* w, double* acc, void* stream);
+int vmp_decoder_loglike_f64(int64_t N, int K, int S, int Dobs, int mode, const double* y, const double* means,
+                            const double* out2, const double* w, double* acc, void* stream);
+
+/* General dense-natural-parameter Gaussian log-density (API surface of distributions/gaussian.py).
+ * S == 0: gaussian.log_probability_nat (gaussian.py:30-71): x[N,D], eta1[N,K,D], eta2[N,K,D,D], log_w[K] or NULL
+ *         -> out[N,K] normalised over K.   S >= 1: gaussian.log_probability_nat_per_samp (74-105):
+ *         x[N,K,S,D] -> out[N,K,S].                                                                      */
+int vmp_gaussian_logprob_nat_f32(int64_t N, int K, int S, int D, const float* x, const float* eta1,
+                                 const float* eta2, const float* log_w, float* out, void* stream);
+int vmp_gaussian_logprob_nat_f64(int64_t N, int K, int S, int D, const double* x, const double* eta1,
+                                 const double* eta2, const double* log_w, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMP_SVAE_H */

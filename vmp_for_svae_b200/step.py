@@ -1,0 +1,79 @@
+"""The fused hot path: one `SVAEStep.step()` = local VMP step over this rank's shard of points + global
+natural-gradient update (experiments.py:208-260 in one allocation-free sequence of kernel launches):
+
+    phi_prepare, theta_prepare  (K-sized prologues)
+    local_step                  log r, selected sample x[n, z_n, 0], ELBO-regulariser partials
+    suffstats                   [N_k, sum r x, sum r x x^T] of this shard, double
+    all-reduce (NCCL)           the packed K*(D^2+D+2)+4 doubles — the only exchange of the step
+    ng_update                   theta <- (1-rho) theta + rho (prior + stats)   (identical on every rank)
+
+Points are sharded contiguously across ranks, phi_gmm / theta / prior are replicated.  The ELBO is evaluated with
+theta BEFORE the update (the reference leaves the order undefined; the oracle fixes the same order).
+"""
+import torch
+
+from . import core, _lib
+
+
+class SVAEStep(object):
+    def __init__(self, N_local, K, D, S=1, dtype=torch.float32, device='cuda', den_mode=core.DEN_GAUSS,
+                 process_group=None, use_dist=None):
+        self.N, self.K, self.D, self.S = int(N_local), int(K), int(D), int(S)
+        self.dtype, self.device, self.den_mode = dtype, torch.device(device), den_mode
+        plen, tlen, slen = _lib.record_lens(D)
+        e = lambda *s, dt=dtype: torch.empty(*s, dtype=dt, device=self.device)
+        self.phi_rec, self.theta_rec = e(K, plen), e(K, tlen)
+        self.log_r, self.x_sample = e(self.N, K), e(self.N, D)
+        self.z = e(self.N, dt=torch.int32)
+        # one contiguous double buffer: [stats K*slen | elbo 4] -> a single all-reduce
+        self.red = torch.zeros(K * slen + 4, dtype=torch.float64, device=self.device)
+        self.stats = self.red[:K * slen].view(K, slen)
+        self.elbo_acc = self.red[K * slen:]
+        self.pg = process_group
+        if use_dist is None:
+            use_dist = torch.distributed.is_available() and torch.distributed.is_initialized() and \
+                torch.distributed.get_world_size(process_group) > 1
+        self.use_dist = bool(use_dist)
+        self.launches_per_step = 7      # phi, theta, local_step, select_sample, suffstats, ng_update (+ memset)
+
+    def step(self, phi_enc, phi_gmm, theta, prior, rho, seed=0, noise=None, u=None, only_alpha=False,
+             kernel_events=None):
+        """Runs one step; mutates `theta` in place; returns dict(log_r, x_sample, z, elbo_acc) (device tensors,
+        valid on the current stream).  elbo_acc = [sum r*num, sum r*den, regulariser, #bad pivots] over ALL ranks."""
+        eta1, eta2_diag = phi_enc
+        core.phi_prepare(phi_gmm[0], phi_gmm[1], phi_gmm[2], out=self.phi_rec)
+        if self.den_mode == core.DEN_GAUSS:
+            core.theta_prepare_gauss(theta, out=self.theta_rec)
+        else:
+            core.theta_prepare_student(theta, out=self.theta_rec)
+        self.red.zero_()
+        if kernel_events is not None:       # CUDA events bracketing the dominant kernel (bench.py roofline)
+            kernel_events[0].record()
+        core.local_step(eta1, eta2_diag, self.phi_rec, self.theta_rec, self.S, den_mode=self.den_mode, noise=noise,
+                        u=u, seed=seed, log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc)
+        if kernel_events is not None:
+            kernel_events[1].record()
+        core.suffstats(self.x_sample, self.log_r, r_is_log=True, stats=self.stats)
+        if self.use_dist:
+            torch.distributed.all_reduce(self.red, group=self.pg)
+        if only_alpha:
+            core.ng_update(self.stats, rho, [prior[0]], [theta[0]], only_alpha=True)
+        else:
+            core.ng_update(self.stats, rho, prior, theta)
+        return dict(log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc)
+
+
+def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, staging=None, chunk=None):
+    """End-to-end form of the step for HOST-resident encoder outputs (pinned CPU tensors): copies this rank's
+    eta1 / eta2_diag to the device, runs `stepper.step`, and reads the step's results (ELBO terms and the updated
+    theta's alpha) back to the host.  Returns (elbo_terms ndarray[4], alpha ndarray[K])."""
+    eta1_h, eta2_h = phi_enc_host
+    if staging is None:
+        staging = (torch.empty(eta1_h.shape, dtype=eta1_h.dtype, device=stepper.device),
+                   torch.empty(eta2_h.shape, dtype=eta2_h.dtype, device=stepper.device))
+    staging[0].copy_(eta1_h, non_blocking=True)
+    staging[1].copy_(eta2_h, non_blocking=True)
+    out = stepper.step(staging, phi_gmm, theta, prior, rho, seed=seed)
+    elbo = out['elbo_acc'].to('cpu', non_blocking=False)
+    alpha = theta[0].to('cpu')
+    return elbo.numpy(), alpha.numpy()
