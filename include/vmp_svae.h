@@ -77,7 +77,8 @@ int vmp_theta_prepare_student_f64(int K, int D, const double* alpha, const doubl
  * in : eta1[N,D], eta2_diag[N,D] (<0)  encoder natural parameters
  *      phi_rec, theta_rec               from the prologues; den_mode VMP_DEN_*
  *      noise[N,K,D,S] or NULL           injected raw noise (svae.py:113-114 layout); NULL -> Philox(seed)
- *      u[N] or NULL                     injected uniforms of the categorical draw; NULL -> Philox(seed)
+ *      gumbel_u[N,K] or NULL            injected uniforms of the categorical draw z_n = argmax_k(log r_nk -
+ *                                       log(-log u_nk)) (tf.multinomial's GPU algorithm); NULL -> Philox(seed)
  *      x_in[N,K,S,D] or NULL            evaluate these samples instead of drawing (svae.compute_elbo called with
  *                                       caller-supplied x_k_samps); eps is recovered as a + L^T (x - mu1)
  * out: log_r[N,K]                       normalised log q(z|y)         (may not be NULL)
@@ -87,17 +88,20 @@ int vmp_theta_prepare_student_f64(int K, int D, const double* alpha, const doubl
  *                                       regulariser = mean_s sum r (num - den), number of non-PD pivots   */
 int vmp_svae_local_step_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                             const float* phi_rec, const float* theta_rec, int den_mode,
-                            const float* noise, const float* u, uint64_t seed, const float* x_in,
+                            const float* noise, const float* gumbel_u, uint64_t seed, const float* x_in,
                             float* log_r, float* x_sample, int32_t* z, float* x_k_samples,
-                            double* elbo_acc, void* stream);
+                            double* elbo_acc, void* workspace, size_t workspace_bytes, void* stream);
 int vmp_svae_local_step_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
                             const double* phi_rec, const double* theta_rec, int den_mode,
-                            const double* noise, const double* u, uint64_t seed, const double* x_in,
+                            const double* noise, const double* gumbel_u, uint64_t seed, const double* x_in,
                             double* log_r, double* x_sample, int32_t* z, double* x_k_samples,
-                            double* elbo_acc, void* stream);
+                            double* elbo_acc, void* workspace, size_t workspace_bytes, void* stream);
+/* Caller-provided scratch for the step (staged per-component records of the fp32 fast path, D in {16,32,64});
+ * without it (NULL / too small) the generic thread-per-pair kernels run instead.                       */
+size_t vmp_svae_local_step_workspace_bytes(int K, int D);
 
 /* The noise the in-kernel generator uses for a given seed, written in the reference layout
- * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N] (either may be NULL).        */
+ * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N,K] (either may be NULL).      */
 int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, float* noise, float* u, void* stream);
 int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, double* noise, double* u, void* stream);
 

@@ -81,10 +81,22 @@ def multinomial_inverse_cdf(logits, u):
     return z.clamp_(max=logits.shape[1] - 1)
 
 
-def subsample_x(x_k_samples, log_q_z_given_y, u):
-    """svae.py:122-151 : pick x_k_samples[n, z_ns, s], z_ns ~ Cat(softmax(log q)) -> [N,S,L]."""
+def multinomial_gumbel_max(logits, gumbel_u):
+    """tf.multinomial's GPU kernel (multinomial_op_gpu.cu.cc) with injected uniforms gumbel_u[N,S,K]:
+    z_ns = argmax_k(logit_nk - log(-log(u_nsk))) (first maximum on ties)."""
+    g = -torch.log(-torch.log(gumbel_u.to(logits.dtype)))
+    return torch.argmax(logits.unsqueeze(1) + g, dim=2)
+
+
+def subsample_x(x_k_samples, log_q_z_given_y, u=None, gumbel_u=None):
+    """svae.py:122-151 : pick x_k_samples[n, z_ns, s], z_ns ~ Cat(softmax(log q)) -> [N,S,L].
+    The draw is tf.multinomial: its CPU kernel is an inverse-CDF search (inject u[N,S]), its GPU kernel a
+    Gumbel-max (inject gumbel_u[N,S,K]); both sample the same categorical."""
     N, K, S, L = x_k_samples.shape
-    z = multinomial_inverse_cdf(log_q_z_given_y, u)                      # N,S
+    if gumbel_u is not None:
+        z = multinomial_gumbel_max(log_q_z_given_y, gumbel_u)
+    else:
+        z = multinomial_inverse_cdf(log_q_z_given_y, u)                  # N,S
     n_idx = torch.arange(N).reshape(-1, 1).expand(N, S)
     s_idx = torch.arange(S).reshape(1, -1).expand(N, S)
     return x_k_samples[n_idx, z, s_idx], z
@@ -249,13 +261,19 @@ def init_recognition_params(theta, nb_components, normal=None):
 
 
 # ---------------------------------------------------------------------------- whole step
-def svae_step(phi_enc, phi_gmm, theta, prior, noise, u, rho):
+def svae_step(phi_enc, phi_gmm, theta, prior, noise, u, rho, gumbel_u=None):
     """One pass of the hot path in the order the reference graph runs it
     (experiments.py:208-260; ELBO reads theta BEFORE the update):
       e_step -> subsample_x[:,0,:] -> ELBO regulariser -> m_step -> update_gmm_params.
+    u[N,S]: inverse-CDF uniforms, or gumbel_u[N,K] (sample 0 only): Gumbel-max uniforms.
     Returns dict(log_r, x_samples, z, reg, num, den, theta_new)."""
     x_k, log_r, phi_tilde, _ = e_step(phi_enc, phi_gmm, noise)
-    xs, z = subsample_x(x_k, log_r, u)
+    if gumbel_u is not None:
+        S = x_k.shape[2]
+        gu = gumbel_u.unsqueeze(1).expand(-1, S, -1)
+        xs, z = subsample_x(x_k, log_r, gumbel_u=gu)
+    else:
+        xs, z = subsample_x(x_k, log_r, u)
     x_samples = xs[:, 0, :]
     N, K = log_r.shape
     dt = log_r.dtype

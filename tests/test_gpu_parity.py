@@ -149,24 +149,26 @@ def _oracle_inputs(N, K, D, S, seed, spread):
     p1 = np.logaddexp(0.0, rs.randn(N, D))
     mu1 = centres.numpy()[rs.randint(0, K, N)] * (0.2 + 0.8 * rs.rand(N, 1)) + spread * rs.randn(N, D)
     eta1, eta2d = T(mu1 * p1), T(-0.5 * p1)
-    noise, u = T(rs.randn(N, K, D, S)), T(rs.rand(N))
+    noise, u = T(rs.randn(N, K, D, S)), T(rs.rand(N, K))
     return prior, theta, (mu_k, L_k, pi_k), (eta1, eta2d), noise, u
 
 
 STEP_SHAPES = [(100, 10, 2, 10), (274, 10, 6, 10), (257, 32, 8, 2), (96, 7, 16, 1), (64, 12, 32, 1), (40, 9, 64, 1),
-               (33, 5, 11, 3), (1, 3, 4, 1), (130, 1, 5, 2)]
+               (33, 5, 11, 3), (1, 3, 4, 1), (130, 1, 5, 2), (67, 5, 16, 3), (50, 3, 32, 2), (19, 4, 64, 2),
+               (300, 20, 24, 1)]
 
 
 @pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
 @pytest.mark.parametrize('shape', STEP_SHAPES, ids=lambda s: 'N%dK%dD%dS%d' % s)
 def test_fused_step_vs_oracle(shape, dt):
-    """SVAEStep.step (what bench.py times) against oracle.svae_step on identical inputs and injected noise."""
+    """SVAEStep.step (what bench.py times) against oracle.svae_step on identical inputs and injected noise.
+    fp32 with D in {16,32,64} runs the register-resident group engine, everything else the generic kernels."""
     from oracle import svae_port
     from vmp_for_svae_b200.step import SVAEStep
     N, K, D, S = shape
     prior, theta, phi_gmm, phi_enc, noise, u = _oracle_inputs(N, K, D, S, seed=N + K + D, spread=0.3)
     rho = 0.2
-    ref = svae_port.svae_step(phi_enc, phi_gmm, [t.clone() for t in theta], prior, noise, u.unsqueeze(1).expand(N, S).contiguous(), rho)
+    ref = svae_port.svae_step(phi_enc, phi_gmm, [t.clone() for t in theta], prior, noise, None, rho, gumbel_u=u)
     dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
     th = dev(theta)
     st = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False)
@@ -207,6 +209,36 @@ def test_inkernel_noise_equals_injected_noise():
     assert torch.equal(oa['x_sample'], ob['x_sample'])
     for x, y in zip(th_a, th_b):
         torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('shape', [(777, 9, 16, 2), (515, 17, 32, 1), (203, 11, 64, 2)], ids=lambda s: 'N%dK%dD%dS%d' % s)
+@pytest.mark.parametrize('tma', [True, False], ids=['tma', 'cpasync'])
+def test_group_engine_equals_generic_kernels(shape, tma, monkeypatch):
+    """The register-resident group engine (TMA-staged and cp.async-staged) against the generic thread-per-pair kernels
+    on the same in-kernel noise stream: same z, same samples, log r / ELBO within fp32 rounding."""
+    from vmp_for_svae_b200 import core
+    N, K, D, S = shape
+    dt = torch.float32
+    prior, theta, phi_gmm, phi_enc, _, _ = _oracle_inputs(N, K, D, S, seed=D, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    pe, pg, th = dev(phi_enc), dev(phi_gmm), dev(theta)
+    phi_rec, theta_rec = core.phi_prepare(*pg), core.theta_prepare_gauss(th)
+    monkeypatch.setenv('VMP_FORCE_GENERIC', '1')
+    ref = core.local_step(pe[0], pe[1], phi_rec, theta_rec, S, seed=77, materialize_x_k=True)
+    monkeypatch.setenv('VMP_FORCE_GENERIC', '0')
+    monkeypatch.setenv('VMP_NO_TMA', '0' if tma else '1')
+    out = core.local_step(pe[0], pe[1], phi_rec, theta_rec, S, seed=77, materialize_x_k=True)
+    torch.cuda.synchronize()
+    rt = rtol_for(dt, D)
+    check('engine r_nk', torch.exp(out['log_r']), torch.exp(ref['log_r']), rt, 1e-3, shape=list(shape), tma=tma)
+    check('engine x_k', out['x_k_samples'], ref['x_k_samples'], rt, 1.0, shape=list(shape), tma=tma)
+    agree = (out['z'] == ref['z']).double().mean().item()
+    assert agree >= 0.99, agree
+    m = out['z'] == ref['z']
+    check('engine x_sample', out['x_sample'][m], ref['x_sample'][m], rt, 1.0, shape=list(shape), tma=tma)
+    scale = float(ref['elbo_acc'][:2].abs().max())
+    check('engine elbo', out['elbo_acc'][:3], ref['elbo_acc'][:3], rt, scale, shape=list(shape), tma=tma)
+    assert float(out['elbo_acc'][3]) == 0.0
 
 
 @pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])

@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol():
     from vmp_for_svae_b200 import _lib
     lib = _lib.load()
     header = open(os.path.join(ROOT, 'include', 'vmp_svae.h')).read()
-    declared = sorted(set(re.findall(r'^int\s+(vmp_\w+)\s*\(', header, flags=re.M)))
+    declared = sorted(set(re.findall(r'^(?:int|size_t)\s+(vmp_\w+)\s*\(', header, flags=re.M)))
     assert len(declared) >= 28
     for name in declared:
         assert hasattr(lib, name), 'libvmp_svae.so does not export %s' % name

@@ -19,7 +19,7 @@ _SIGS_T = {
     'vmp_theta_prepare_gauss': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_theta_prepare_student': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_svae_local_step': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_u64, c_ptr,
-                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
+                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr],
     'vmp_fill_noise': [c_i64, c_int, c_int, c_int, c_u64, c_ptr, c_ptr, c_ptr],
     'vmp_suffstats': [c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr],
     'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_int] + [c_ptr] * 15 + [c_ptr],
@@ -34,6 +34,7 @@ _SIGS = {
     'vmp_phi_record_len': [c_int],
     'vmp_theta_record_len': [c_int],
     'vmp_stats_len': [c_int],
+    'vmp_svae_local_step_workspace_bytes': [c_int, c_int],
 }
 EXPORTS = sorted(list(_SIGS) + [n + s for n in _SIGS_T for s in ('_f32', '_f64')])
 
@@ -59,7 +60,7 @@ def load(build_if_missing=True):
     lib = ctypes.CDLL(_LIB_PATH)
     for name, args in _SIGS.items():
         fn = getattr(lib, name)
-        fn.argtypes, fn.restype = args, c_int
+        fn.argtypes, fn.restype = args, (ctypes.c_size_t if name.endswith('_bytes') else c_int)
     for name, args in _SIGS_T.items():
         for suf in ('_f32', '_f64'):
             fn = getattr(lib, name + suf, None)

@@ -58,10 +58,18 @@ def theta_prepare_student(theta, out=None):
     return rec
 
 
+def local_step_workspace(K, D, device):
+    """Scratch the fast path of the local step needs (staged per-component records)."""
+    lib = _lib.load()
+    nbytes = int(lib.vmp_svae_local_step_workspace_bytes(K, D))
+    return torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+
+
 def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise=None, u=None, seed=0, x_in=None,
                want_x_sample=True, want_z=True, materialize_x_k=False, log_r=None, x_sample=None, z=None,
-               elbo_acc=None):
-    """The fused local step.  Returns dict(log_r, x_sample, z, x_k_samples, elbo_acc[4] double)."""
+               elbo_acc=None, workspace=None):
+    """The fused local step.  Returns dict(log_r, x_sample, z, x_k_samples, elbo_acc[4] double).
+    u: uniforms[N,K] of the Gumbel-max categorical draw (None -> in-kernel Philox keyed by `seed`)."""
     N, D = eta1.shape
     K = phi_rec.shape[0]
     dt, dev = eta1.dtype, eta1.device
@@ -71,7 +79,7 @@ def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise
     if noise is not None:
         noise = _chk(noise, (N, K, D, S), dt, 'noise')
     if u is not None:
-        u = _chk(u, (N,), dt, 'u')
+        u = _chk(u, (N, K), dt, 'u (gumbel uniforms)')
     if x_in is not None:
         x_in = _chk(x_in, (N, K, S, D), dt, 'x_k_samps')
     log_r = log_r if log_r is not None else torch.empty(N, K, dtype=dt, device=dev)
@@ -82,15 +90,18 @@ def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise
     x_k = torch.empty(N, K, S, D, dtype=dt, device=dev) if materialize_x_k else None
     if elbo_acc is None:
         elbo_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+    if workspace is None and dt == torch.float32 and x_in is None:
+        workspace = local_step_workspace(K, D, dev)
+    wbytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
     _lib.call('vmp_svae_local_step', dt, N, K, D, S, ptr(eta1), ptr(eta2_diag), ptr(phi_rec), ptr(theta_rec),
               int(den_mode), ptr(noise), ptr(u), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(x_in), ptr(log_r), ptr(x_sample),
-              ptr(z), ptr(x_k), ptr(elbo_acc), stream_ptr(dev))
+              ptr(z), ptr(x_k), ptr(elbo_acc), ptr(workspace), wbytes, stream_ptr(dev))
     return dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=x_k, elbo_acc=elbo_acc)
 
 
 def fill_noise(N, K, D, S, seed, dtype, device, want_noise=True, want_u=True):
     noise = torch.empty(N, K, D, S, dtype=dtype, device=device) if want_noise else None
-    u = torch.empty(N, dtype=dtype, device=device) if want_u else None
+    u = torch.empty(N, K, dtype=dtype, device=device) if want_u else None
     _lib.call('vmp_fill_noise', dtype, N, K, D, S, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(noise), ptr(u),
               stream_ptr(device))
     return noise, u

@@ -112,10 +112,13 @@ __device__ __forceinline__ float philox_normal1(uint64_t seed, uint64_t pair, ui
     const uint32_t c = d & 3u;
     return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
 }
-__device__ __forceinline__ float philox_uniform_point(uint64_t seed, uint64_t n) {
-    const uint4 r = Philox::gen(make_uint4((uint32_t)n, (uint32_t)(n >> 32), 0x5eedu, 0xca7u),
+// the uniform behind the Gumbel-max categorical draw of pair (n,k) — the in-kernel definition of u[n,k]
+__device__ __forceinline__ float philox_uniform_pair(uint64_t seed, uint64_t pair) {
+    const uint4 r = Philox::gen(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), 0x5eedu, 0xca7u),
                                 make_uint2((uint32_t)seed ^ 0xA511E9B3u, (uint32_t)(seed >> 32)));
     return u32_to_unit(r.x);
 }
+// Gumbel(0,1) from a uniform: tf.multinomial's GPU kernel draws z = argmax_k(logit_k - log(-log(u_k)))
+template <typename T> __device__ __forceinline__ T gumbel_from_uniform(T u) { return -t_log(-t_log(u)); }
 
 }  // namespace vmp

@@ -1,12 +1,19 @@
-// local_step.cu — the fused local VMP step (svae.e_step + subsample_x + ELBO regulariser).
+// local_step.cu — the fused local VMP step (svae.e_step + subsample_x + ELBO regulariser): entry points, dispatch,
+// and the generic thread-per-pair kernels.
 //
-// Kernel A  local_step_kernel : one thread per (point, component) pair inside a CTA tile of PTS points x K
-//           components; per-pair Cholesky/solves/samples/ELBO terms (pair_math.cuh), then a per-point
-//           log-sum-exp over the K scores held in shared memory, log_r written coalesced, ELBO partials
-//           block-reduced in double and atomically accumulated.
-// Kernel B  select_sample_kernel : one thread per point; inverse-CDF pick of z_n from log_r (double cdf, the
-//           tf.multinomial CPU algorithm) and re-evaluation of the selected pair for x[n, z_n, 0].
+// Two implementations of the same arithmetic (pair_math.cuh states it):
+//   * fast  (local_step_fast.cuh): fp32, D in {16, 32, 64}: register-resident group engine, TMA-staged records,
+//           online Gumbel-max selection — the path bench.py measures;
+//   * generic (this file): any D <= 64, fp32/fp64, one thread per (point, component) pair; D <= 8 fully unrolled in
+//           registers (the C1-C3 shapes), larger D through local memory.  Kernel A computes scores / samples / ELBO
+//           terms and the per-point log-sum-exp; kernel B draws z_n by Gumbel-max from log_r and re-evaluates the
+//           selected pair for x[n, z_n, 0].
+// The categorical draw follows tf.multinomial's GPU kernel (multinomial_op_gpu.cu.cc): z = argmax_k(logit_k + G_k),
+// G_k = -log(-log(u_k)); u[N,K] may be injected for parity tests, otherwise Philox(seed, pair).
+#include "local_step_fast.cuh"
 #include "pair_math.cuh"
+
+#include <cstdlib>
 
 namespace vmp {
 
@@ -123,34 +130,24 @@ local_step_kernel(int64_t N, int K, int Drt, int S, int PTS,
     }
 }
 
-// z = upper_bound(cdf, u * total), cdf = cumsum(exp(log_r - max)) in double (tf.multinomial CPU kernel)
-template <typename T>
-__device__ __forceinline__ int pick_component(const T* __restrict__ lr, int K, double u) {
-    double mx = (double)lr[0];
-    for (int k = 1; k < K; ++k) mx = fmax(mx, (double)lr[k]);
-    double total = 0.0;
-    for (int k = 0; k < K; ++k) total += exp((double)lr[k] - mx);
-    const double target = u * total;
-    double c = 0.0;
-    int z = K - 1;
-    for (int k = 0; k < K; ++k) {
-        c += exp((double)lr[k] - mx);
-        if (c > target) { z = k; break; }
-    }
-    return z;
-}
-
 template <typename T, int DT>
 __global__ void __launch_bounds__(LS_THREADS)
 select_sample_kernel(int64_t N, int K, int Drt, int S, const T* __restrict__ eta1, const T* __restrict__ eta2d,
-                     const T* __restrict__ phi_rec, const T* __restrict__ log_r, const T* __restrict__ u,
+                     const T* __restrict__ phi_rec, const T* __restrict__ log_r, const T* __restrict__ gum_u,
                      NoiseSrc<T> nz, T* __restrict__ x_sample, int32_t* __restrict__ z_out) {
     using PM = PairMath<T, DT>;
     const int D = DT ? DT : Drt;
     const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
-    const double un = u != nullptr ? (double)u[n] : (double)philox_uniform_point(nz.seed, (uint64_t)n);
-    const int z = pick_component(log_r + n * K, K, un);
+    // Gumbel-max: first arg-max of log_r + G (normalisation does not move the arg-max)
+    int z = 0;
+    T best = -CUDART_INF_F;
+    for (int k = 0; k < K; ++k) {
+        const uint64_t pair = (uint64_t)n * K + k;
+        const T u = gum_u != nullptr ? gum_u[pair] : (T)philox_uniform_pair(nz.seed, pair);
+        const T cand = log_r[pair] + gumbel_from_uniform<T>(u);
+        if (cand > best) { best = cand; z = k; }
+    }
     if (z_out != nullptr) z_out[n] = z;
     if (x_sample == nullptr) return;
     PM pm;
@@ -165,22 +162,23 @@ select_sample_kernel(int64_t N, int K, int Drt, int S, const T* __restrict__ eta
 template <typename T>
 __global__ void fill_noise_kernel(int64_t N, int K, int D, int S, uint64_t seed, T* noise, T* u) {
     const int64_t total = N * K * (int64_t)D * S;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        if (noise == nullptr) break;
-        const int s = (int)(e % S);
-        const int d = (int)((e / S) % D);
-        const int64_t pair = e / ((int64_t)S * D);
-        noise[e] = (T)philox_normal1(seed, (uint64_t)pair, (uint32_t)s, (uint32_t)d);
-    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (noise != nullptr)
+        for (int64_t e = t0; e < total; e += stride) {
+            const int s = (int)(e % S);
+            const int d = (int)((e / S) % D);
+            const int64_t pair = e / ((int64_t)S * D);
+            noise[e] = (T)philox_normal1(seed, (uint64_t)pair, (uint32_t)s, (uint32_t)d);
+        }
     if (u != nullptr)
-        for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
-            u[n] = (T)philox_uniform_point(seed, (uint64_t)n);
+        for (int64_t pr = t0; pr < N * K; pr += stride) u[pr] = (T)philox_uniform_pair(seed, (uint64_t)pr);
 }
 
 template <typename T, int DT>
-static int launch_local_step(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* phi_rec,
-                             const T* theta_rec, int den_mode, const T* noise, const T* u, uint64_t seed, const T* x_in,
-                             T* log_r, T* x_sample, int32_t* z, T* x_k_samples, double* elbo_acc, cudaStream_t st) {
+static int launch_generic(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* phi_rec,
+                          const T* theta_rec, int den_mode, const T* noise, const T* gum_u, uint64_t seed,
+                          const T* x_in, T* log_r, T* x_sample, int32_t* z, T* x_k_samples, double* elbo_acc,
+                          cudaStream_t st) {
     NoiseSrc<T> nz{noise, seed, K, D, S};
     int PTS = LS_THREADS / K;
     if (PTS < 1) PTS = 1;
@@ -198,32 +196,82 @@ static int launch_local_step(int64_t N, int K, int D, int S, const T* eta1, cons
     if (int e = launch_status()) return e;
     if (x_sample != nullptr || z != nullptr) {
         const int64_t g2 = (N + LS_THREADS - 1) / LS_THREADS;
-        select_sample_kernel<T, DT><<<(unsigned)g2, LS_THREADS, 0, st>>>(N, K, D, S, eta1, eta2d, phi_rec, log_r, u, nz,
-                                                                       x_sample, z);
+        select_sample_kernel<T, DT><<<(unsigned)g2, LS_THREADS, 0, st>>>(N, K, D, S, eta1, eta2d, phi_rec, log_r,
+                                                                       gum_u, nz, x_sample, z);
         if (int e = launch_status()) return e;
     }
     return VMP_OK;
 }
 
+static size_t fast_workspace_bytes(int K, int D) {
+    if (D != 16 && D != 32 && D != 64) return 0;
+    return sizeof(float) * (size_t)K * fast_rec_len(D);
+}
+
+static bool fast_enabled() {
+    const char* e = std::getenv("VMP_FORCE_GENERIC");
+    return !(e && e[0] == '1');
+}
+static bool tma_enabled() {
+    const char* e = std::getenv("VMP_NO_TMA");
+    return !(e && e[0] == '1');
+}
+
+// fp32 fast path when the shape qualifies; returns -100 when it does not
+static int try_fast(int64_t N, int K, int D, int S, const float* eta1, const float* eta2d, const float* phi_rec,
+                    const float* theta_rec, int den_mode, const float* noise, const float* gum_u, uint64_t seed,
+                    const float* x_in, float* log_r, float* x_sample, int32_t* z, float* x_k_samples,
+                    double* elbo_acc, void* work, size_t work_bytes, cudaStream_t st) {
+    if (!fast_enabled() || x_in != nullptr || work == nullptr) return -100;
+    const size_t need = fast_workspace_bytes(K, D);
+    if (need == 0 || work_bytes < need) return -100;
+    size_t smem = D == 64 ? fast_smem_bytes<64>(K) : D == 32 ? fast_smem_bytes<32>(K) : fast_smem_bytes<16>(K);
+    const int minb = D == 64 ? 1 : 2;
+    if (smem * minb > 220 * 1024) return -100;
+    float* recs = static_cast<float*>(work);
+    pack_fast_records_kernel<<<K, 256, 0, st>>>(K, D, phi_rec, theta_rec, recs);
+    if (int e = launch_status()) return e;
+    FastParams p{N, K, S, den_mode, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
+    const bool tma = tma_enabled();
+    if (D == 64) return launch_fast<64>(p, tma, st);
+    if (D == 32) return launch_fast<32>(p, tma, st);
+    return launch_fast<16>(p, tma, st);
+}
+template <typename T>
+static int try_fast_t(int64_t, int, int, int, const T*, const T*, const T*, const T*, int, const T*, const T*, uint64_t,
+                      const T*, T*, T*, int32_t*, T*, double*, void*, size_t, cudaStream_t) {
+    return -100;
+}
+template <>
+int try_fast_t<float>(int64_t N, int K, int D, int S, const float* a, const float* b, const float* c, const float* d,
+                      int m, const float* e, const float* f, uint64_t seed, const float* g, float* h, float* i,
+                      int32_t* z, float* j, double* acc, void* work, size_t wb, cudaStream_t st) {
+    return try_fast(N, K, D, S, a, b, c, d, m, e, f, seed, g, h, i, z, j, acc, work, wb, st);
+}
+
 template <typename T>
 int svae_local_step(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* phi_rec,
-                    const T* theta_rec, int den_mode, const T* noise, const T* u, uint64_t seed, const T* x_in,
-                    T* log_r, T* x_sample, int32_t* z, T* x_k_samples, double* elbo_acc, void* stream) {
-    if (N < 0 || K <= 0 || S <= 0 || !eta1 || !eta2d || !phi_rec || !theta_rec || !log_r || !elbo_acc)
-        return VMP_E_BADARG;
+                    const T* theta_rec, int den_mode, const T* noise, const T* gum_u, uint64_t seed, const T* x_in,
+                    T* log_r, T* x_sample, int32_t* z, T* x_k_samples, double* elbo_acc, void* work, size_t work_bytes,
+                    void* stream) {
+    if (N < 0 || K <= 0 || S <= 0) return VMP_E_BADARG;
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     if (den_mode != VMP_DEN_GAUSS && den_mode != VMP_DEN_STUDENT) return VMP_E_BADMODE;
     if (N == 0) return VMP_OK;
+    if (!eta1 || !eta2d || !phi_rec || !theta_rec || !log_r || !elbo_acc) return VMP_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
+    const int rc = try_fast_t<T>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed, x_in, log_r,
+                                 x_sample, z, x_k_samples, elbo_acc, work, work_bytes, st);
+    if (rc != -100) return rc;
 #define VMP_LS(DD)                                                                                              \
     case DD:                                                                                                    \
-        return launch_local_step<T, DD>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, u, seed,  \
-                                        x_in, log_r, x_sample, z, x_k_samples, elbo_acc, st)
+        return launch_generic<T, DD>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed, \
+                                     x_in, log_r, x_sample, z, x_k_samples, elbo_acc, st)
     switch (D) {
         VMP_LS(1); VMP_LS(2); VMP_LS(3); VMP_LS(4); VMP_LS(5); VMP_LS(6); VMP_LS(7); VMP_LS(8);
         default:
-            return launch_local_step<T, 0>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, u, seed,
-                                           x_in, log_r, x_sample, z, x_k_samples, elbo_acc, st);
+            return launch_generic<T, 0>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed, x_in,
+                                        log_r, x_sample, z, x_k_samples, elbo_acc, st);
     }
 #undef VMP_LS
 }
@@ -238,19 +286,27 @@ int fill_noise(int64_t N, int K, int D, int S, uint64_t seed, T* noise, T* u, vo
 }  // namespace vmp
 
 extern "C" {
+size_t vmp_svae_local_step_workspace_bytes(int K, int D) {
+    const size_t b = vmp::fast_workspace_bytes(K, D);
+    return b ? b : 16;
+}
 int vmp_svae_local_step_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                             const float* phi_rec, const float* theta_rec, int den_mode, const float* noise,
-                            const float* u, uint64_t seed, const float* x_in, float* log_r, float* x_sample,
-                            int32_t* z, float* x_k_samples, double* elbo_acc, void* stream) {
-    return vmp::svae_local_step<float>(N, K, D, S, eta1, eta2_diag, phi_rec, theta_rec, den_mode, noise, u, seed, x_in,
-                                       log_r, x_sample, z, x_k_samples, elbo_acc, stream);
+                            const float* gumbel_u, uint64_t seed, const float* x_in, float* log_r, float* x_sample,
+                            int32_t* z, float* x_k_samples, double* elbo_acc, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    return vmp::svae_local_step<float>(N, K, D, S, eta1, eta2_diag, phi_rec, theta_rec, den_mode, noise, gumbel_u, seed,
+                                       x_in, log_r, x_sample, z, x_k_samples, elbo_acc, workspace, workspace_bytes,
+                                       stream);
 }
 int vmp_svae_local_step_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
                             const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
-                            const double* u, uint64_t seed, const double* x_in, double* log_r, double* x_sample,
-                            int32_t* z, double* x_k_samples, double* elbo_acc, void* stream) {
-    return vmp::svae_local_step<double>(N, K, D, S, eta1, eta2_diag, phi_rec, theta_rec, den_mode, noise, u, seed, x_in,
-                                        log_r, x_sample, z, x_k_samples, elbo_acc, stream);
+                            const double* gumbel_u, uint64_t seed, const double* x_in, double* log_r, double* x_sample,
+                            int32_t* z, double* x_k_samples, double* elbo_acc, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    return vmp::svae_local_step<double>(N, K, D, S, eta1, eta2_diag, phi_rec, theta_rec, den_mode, noise, gumbel_u,
+                                        seed, x_in, log_r, x_sample, z, x_k_samples, elbo_acc, workspace,
+                                        workspace_bytes, stream);
 }
 int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, float* noise, float* u, void* stream) {
     return vmp::fill_noise<float>(N, K, D, S, seed, noise, u, stream);

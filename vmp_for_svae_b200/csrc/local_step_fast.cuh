@@ -1,0 +1,515 @@
+// local_step_fast.cuh — the register-resident group engine of the fused local step (fp32, D in {16, 32, 64}).
+//
+// Mapping.  BS lanes of a warp ("group") own one (point n, component k) pair; lane gl owns rows r*BS + gl,
+// r < ROWS = D/BS, of the D x D system.  The lower triangle of P~ = P2_k + diag(p1_n) lives in registers
+// (A[r][c], c < (r+1)*BS; entries right of the diagonal are don't-care slots that are computed but never feed a
+// meaningful value), so the whole factorisation runs out of the register file:
+//   * right-looking Cholesky: at step j the pivot is broadcast with one shuffle, every lane scales its own entries
+//     of column j, publishes them to a 2 x D shared-memory column buffer, and updates its rows with the column read
+//     back as 128-bit broadcasts (FMA : LDS.128 = 4*ROWS : 1);
+//   * the two forward substitutions a = L^-1 P2 d, a1 = L^-1 P1 d ride along as extra right-hand sides;
+//   * back substitution L^T y = eps - a goes block by block (BS x BS) with the blocks transposed through a padded
+//     shared-memory tile, the solved block broadcast through shared memory;
+//   * the theta quadratic form |W_k (x - m_k)|^2 is a row-owned triangular mat-vec against the staged W_k.
+// A CTA of WARPS warps holds PPC = WARPS*32/BS points and walks k = 0..K-1 with all its pairs on the same k, so the
+// per-component record (P2_k | W_k | mu2_k | m_k | scalars, rows padded to D+4 floats: conflict-free 128-bit row
+// reads) is staged ONCE per CTA per k — by a 1-D bulk TMA copy (cp.async.bulk + mbarrier complete_tx) into a
+// double-buffered stage, issued one component ahead.  Per point, the K scores / ELBO terms sit in shared memory until
+// the log-sum-exp; the categorical draw is an online Gumbel-max (tf.multinomial's GPU algorithm), so the selected
+// sample x[n, z_n, 0] is simply the running arg-max's sample and no second pass is needed.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace vmp {
+
+struct FastParams {
+    int64_t N;
+    int K, S, den_mode;
+    const float* eta1;
+    const float* eta2d;
+    const float* recs;      // [K][REC] packed staged records
+    const float* noise;     // [N,K,D,S] or nullptr
+    const float* gum_u;     // [N,K] or nullptr
+    uint64_t seed;
+    float* log_r;
+    float* x_sample;
+    int32_t* z;
+    float* x_k_samples;
+    double* elbo_acc;
+    int64_t ntiles;
+};
+
+template <int D> struct FastGeom {
+    static constexpr int BS = D / 4;                 // lanes per pair (ROWS = 4)
+    static constexpr int LD = D + 4;                 // padded row stride of the staged matrices
+    static constexpr int REC = 2 * D * LD + 2 * D + 8;
+    static constexpr int TS = BS + 4;                // transpose tile stride
+    // group scratch: col[2][D] | vec[D] | ybf[max(BS,4)] | tbf[BS][TS]; kept congruent to BS mod 32 so the groups
+    // of one warp land in different banks
+    static constexpr int GS_RAW = 3 * D + (BS < 4 ? 4 : BS) + BS * TS;
+    static constexpr int GS = ((GS_RAW - BS + 31) / 32) * 32 + BS;
+};
+
+__host__ __device__ inline int fast_rec_len(int D) { return 2 * D * (D + 4) + 2 * D + 8; }
+
+// (phi_rec, theta_rec) of prepare.cu -> padded staged records
+__global__ void pack_fast_records_kernel(int K, int D, const float* __restrict__ phi_rec,
+                                         const float* __restrict__ theta_rec, float* __restrict__ out) {
+    const int k = blockIdx.x;
+    const int LD = D + 4, REC = fast_rec_len(D);
+    const float* pr = phi_rec + (size_t)k * phi_record_len(D);
+    const float* tr = theta_rec + (size_t)k * theta_record_len(D);
+    float* o = out + (size_t)k * REC;
+    for (int e = threadIdx.x; e < D * LD; e += blockDim.x) {
+        const int i = e / LD, c = e - i * LD;
+        o[e] = c < D ? pr[i * D + c] : 0.f;
+        o[D * LD + e] = c < D ? tr[i * D + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        o[2 * D * LD + i] = pr[D * D + i];           // mu2
+        o[2 * D * LD + D + i] = tr[D * D + i];       // m_theta
+    }
+    if (threadIdx.x < 8) {
+        float v = 0.f;
+        if (threadIdx.x == 0) v = pr[D * D + 2 * D];        // log pi
+        if (threadIdx.x == 1) v = pr[D * D + 2 * D + 1];    // logdet P2
+        if (threadIdx.x == 2) v = tr[D * D + D];            // cden
+        if (threadIdx.x == 3) v = tr[D * D + D + 1];        // nu
+        o[2 * D * LD + 2 * D + threadIdx.x] = v;
+    }
+}
+
+// ---- mbarrier / bulk-copy primitives (inline PTX) ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// compile-time loop: the index is a template constant, so every inner bound / register index that depends on it is
+// a constant at instantiation time (a plain `#pragma unroll` nest leaves j-dependent inner loops rolled and pushes
+// the register-resident matrix into local memory)
+template <int I, int N, typename F> __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+template <int I, typename F> __device__ __forceinline__ void static_for_down(F&& f) {   // I-1, ..., 0
+    if constexpr (I > 0) {
+        f(std::integral_constant<int, I - 1>{});
+        static_for_down<I - 1>(f);
+    }
+}
+
+template <int BS> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = BS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, BS);
+    return v;
+}
+template <int BS> __device__ __forceinline__ double group_sum_d(double v) {
+#pragma unroll
+    for (int o = BS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, BS);
+    return v;
+}
+template <int BS> __device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = BS / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, BS));
+    return v;
+}
+
+template <int D, int WARPS, int MINB, bool TMA>
+__global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const FastParams p) {
+    using G = FastGeom<D>;
+    constexpr int BS = G::BS, ROWS = 4, GPW = 32 / BS, PPC = WARPS * GPW, LD = G::LD, REC = G::REC, TS = G::TS;
+    constexpr int GS = G::GS;
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(D % 16 == 0 && BS * ROWS == D, "D must be 16, 32 or 64");
+
+    extern __shared__ __align__(128) unsigned char smraw[];
+    float* stage = reinterpret_cast<float*>(smraw);              // [2][REC]
+    float* gsm = stage + 2 * REC;                                // [PPC][GS]
+    float* ksm = gsm + PPC * GS;                                 // [PPC][K][3]
+    __shared__ __align__(8) uint64_t bars[2];
+    __shared__ double cta_acc[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gl = lane % BS;
+    const int grp = warp * GPW + lane / BS;
+    float* col = gsm + grp * GS;          // [2][D]
+    float* vec = col + 2 * D;             // [D]
+    float* ybf = vec + D;                 // [BS]
+    float* tbf = ybf + (BS < 4 ? 4 : BS); // [BS][TS]
+    float* kst = ksm + (size_t)grp * p.K * 3;
+    const int K = p.K, S = p.S;
+
+    if (tid == 0) {
+        cta_acc[0] = cta_acc[1] = cta_acc[2] = cta_acc[3] = 0.0;
+        if (TMA) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            fence_barrier_init();
+        }
+    }
+    __syncthreads();
+    uint32_t phase0 = 0, phase1 = 0;
+
+    auto issue_load = [&](int k, int buf) {
+        // called by every thread; TMA: one elected thread issues a bulk copy, else: cooperative cp.async
+        const float* src = p.recs + (size_t)k * REC;
+        float* dst = stage + buf * REC;
+        if (TMA) {
+            if (tid == 0) {
+                mbar_expect_tx(&bars[buf], REC * 4);
+                bulk_g2s(dst, src, REC * 4, &bars[buf]);
+            }
+        } else {
+            for (int e = tid; e < REC / 4; e += WARPS * 32) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + 4 * e)), "l"(src + 4 * e)
+                             : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+    };
+
+    for (int64_t tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const int64_t n_raw = tile * PPC + grp;
+        const bool active = n_raw < p.N;
+        const int64_t n = active ? n_raw : p.N - 1;
+
+        float p1[ROWS], mu1[ROWS], xbest[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int row = r * BS + gl;
+            p1[r] = -2.f * p.eta2d[n * D + row];
+            mu1[r] = p.eta1[n * D + row] / p1[r];
+            xbest[r] = 0.f;
+        }
+        float best = -CUDART_INF_F;
+        int zbest = 0;
+        int bad = 0;
+
+        issue_load(0, 0);
+        for (int k = 0; k < K; ++k) {
+            const int buf = k & 1;
+            // stage[buf] holds record k once its copy has landed; the barrier also guarantees that every warp is
+            // done with stage[buf^1] (read at k-1) before record k+1 is copied over it
+            if (TMA) {
+                mbar_wait(&bars[buf], buf ? phase1 : phase0);
+                if (buf) phase1 ^= 1; else phase0 ^= 1;
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+            if (k + 1 < K) issue_load(k + 1, buf ^ 1);
+
+            const float* rec = stage + buf * REC;
+            const float* P2s = rec;
+            const float* Ws = rec + D * LD;
+            const float* mu2 = rec + 2 * D * LD;
+            const float* mth = mu2 + D;
+            const float* scl = mth + D;
+
+            // ---------------- phase 1: d, g1 = P1 d, g = P2 d, A <- P2 rows
+            float g[ROWS], g1[ROWS], a[ROWS], idg[ROWS];
+            float A[ROWS][D];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const int row = r * BS + gl;
+                const float d = mu1[r] - mu2[row];
+                g1[r] = p1[r] * d;
+                vec[row] = d;
+                a[r] = 0.f;
+                idg[r] = 0.f;
+            }
+            __syncwarp();
+            static_for<0, ROWS>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                const float4* prow = reinterpret_cast<const float4*>(P2s + (r * BS + gl) * LD);
+                const float4* dv4 = reinterpret_cast<const float4*>(vec);
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int c4 = 0; c4 < D / 4; ++c4) {
+                    const float4 pv = prow[c4];
+                    const float4 dv = dv4[c4];
+                    s0 = fmaf(pv.x, dv.x, s0);
+                    s1 = fmaf(pv.y, dv.y, s1);
+                    s0 = fmaf(pv.z, dv.z, s0);
+                    s1 = fmaf(pv.w, dv.w, s1);
+                    if (4 * c4 < (r + 1) * BS) {
+                        A[r][4 * c4 + 0] = pv.x;
+                        A[r][4 * c4 + 1] = pv.y;
+                        A[r][4 * c4 + 2] = pv.z;
+                        A[r][4 * c4 + 3] = pv.w;
+                    }
+                }
+                g[r] = s0 + s1;
+            });
+
+            // ---------------- phase 2: right-looking Cholesky with the two forward substitutions riding along
+            float q = 0.f, hl = 0.f, pprod = 1.f;
+            static_for<0, D>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                constexpr int rj = j / BS, lj = j % BS;
+                const float piv = __shfl_sync(FULL, A[rj][j] + p1[rj], lj, BS);
+                bad |= !(piv > 0.f);
+                float inv = rsqrtf(piv);
+                inv = inv * fmaf(-0.5f * piv * inv, inv, 1.5f);          // one Newton step: ~0.5 ulp
+                pprod *= piv;
+                if ((j & 3) == 3) { hl += logf(pprod); pprod = 1.f; }
+                const float yj = __shfl_sync(FULL, g[rj] * inv, lj, BS);
+                const float y1j = __shfl_sync(FULL, g1[rj] * inv, lj, BS);
+                q = fmaf(yj, y1j, q);
+                const bool own = (gl == lj);
+                a[rj] = own ? yj : a[rj];
+                idg[rj] = own ? inv : idg[rj];
+                float* cw = col + (j & 1) * D;
+#pragma unroll
+                for (int r = rj; r < ROWS; ++r) {
+                    float l = A[r][j] * inv;
+                    if (r == rj) l = own ? piv * inv : l;
+                    A[r][j] = l;
+                    cw[r * BS + gl] = l;
+                    g[r] = fmaf(-l, yj, g[r]);
+                    g1[r] = fmaf(-l, y1j, g1[r]);
+                }
+                __syncwarp();
+                const float4* cr4 = reinterpret_cast<const float4*>(cw);
+#pragma unroll
+                for (int c4 = (j + 1) / 4; c4 < D / 4; ++c4) {
+                    const float4 cv = cr4[c4];
+                    const float cvv[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 4 * c4 + e;
+                        if (c > j) {
+#pragma unroll
+                            for (int r = rj; r < ROWS; ++r)
+                                if (c < (r + 1) * BS) A[r][c] = fmaf(-A[r][j], cvv[e], A[r][c]);
+                        }
+                    }
+                }
+            });
+            const float hld = 0.5f * hl;                          // sum_i log L_ii
+            const float score = scl[0] - 0.5f * q + 0.5f * scl[1] - hld;
+
+            // ---------------- phase 3: samples, ELBO terms
+            const uint64_t pair = (uint64_t)n * K + k;
+            float snum = 0.f, sden = 0.f;
+            float x0[ROWS];
+            for (int s = 0; s < S; ++s) {
+                float w[ROWS], y[ROWS];
+                if (p.noise != nullptr) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) w[r] = p.noise[(pair * D + r * BS + gl) * (uint64_t)S + s];
+                } else {
+                    __syncwarp();
+                    for (int qd = gl; qd < D / 4; qd += BS)
+                        reinterpret_cast<float4*>(vec)[qd] = philox_normal4(p.seed, pair, (uint32_t)s, (uint32_t)qd);
+                    __syncwarp();
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) w[r] = vec[r * BS + gl];
+                }
+                float e2 = 0.f;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    e2 = fmaf(w[r], w[r], e2);
+                    w[r] -= a[r];
+                    y[r] = 0.f;
+                }
+                // back substitution, block rows from the bottom
+                static_for_down<ROWS>([&](auto rbc) {
+                    constexpr int rb = decltype(rbc)::value;
+                    __syncwarp();
+#pragma unroll
+                    for (int q4 = 0; q4 < BS / 4; ++q4)
+                        reinterpret_cast<float4*>(tbf + gl * TS)[q4] =
+                            make_float4(A[rb][rb * BS + 4 * q4], A[rb][rb * BS + 4 * q4 + 1], A[rb][rb * BS + 4 * q4 + 2],
+                                        A[rb][rb * BS + 4 * q4 + 3]);
+                    __syncwarp();
+#pragma unroll
+                    for (int i = BS - 1; i >= 0; --i) {
+                        const float t = tbf[i * TS + gl];               // L[rb*BS+i][rb*BS+gl]
+                        const float yi = __shfl_sync(FULL, w[rb] * idg[rb], i, BS);
+                        y[rb] = (gl == i) ? yi : y[rb];
+                        w[rb] = fmaf(-t, yi, w[rb]);
+                    }
+                    if constexpr (rb > 0) {
+                        ybf[gl] = y[rb];
+                        static_for<0, rb>([&](auto rb2c) {
+                            constexpr int rb2 = decltype(rb2c)::value;
+                            __syncwarp();
+#pragma unroll
+                            for (int q4 = 0; q4 < BS / 4; ++q4)
+                                reinterpret_cast<float4*>(tbf + gl * TS)[q4] =
+                                    make_float4(A[rb][rb2 * BS + 4 * q4], A[rb][rb2 * BS + 4 * q4 + 1],
+                                                A[rb][rb2 * BS + 4 * q4 + 2], A[rb][rb2 * BS + 4 * q4 + 3]);
+                            __syncwarp();
+                            float acc = w[rb2];
+#pragma unroll
+                            for (int i4 = 0; i4 < BS / 4; ++i4) {
+                                const float4 yv = reinterpret_cast<const float4*>(ybf)[i4];
+                                acc = fmaf(-tbf[(4 * i4 + 0) * TS + gl], yv.x, acc);
+                                acc = fmaf(-tbf[(4 * i4 + 1) * TS + gl], yv.y, acc);
+                                acc = fmaf(-tbf[(4 * i4 + 2) * TS + gl], yv.z, acc);
+                                acc = fmaf(-tbf[(4 * i4 + 3) * TS + gl], yv.w, acc);
+                            }
+                            w[rb2] = acc;
+                        });
+                    }
+                });
+                // x = mu1 + y ; publish x - m_theta for the quadratic form
+                float x[ROWS];
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    x[r] = mu1[r] + y[r];
+                    vec[r * BS + gl] = x[r] - mth[r * BS + gl];
+                    if (s == 0) x0[r] = x[r];
+                }
+                if (p.x_k_samples != nullptr && active) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) p.x_k_samples[((pair * S) + s) * (uint64_t)D + r * BS + gl] = x[r];
+                }
+                __syncwarp();
+                float q2 = 0.f;
+                static_for<0, ROWS>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
+                    const float4* wrow = reinterpret_cast<const float4*>(Ws + (r * BS + gl) * LD);
+                    const float4* xv4 = reinterpret_cast<const float4*>(vec);
+                    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+                    for (int c4 = 0; c4 < (r + 1) * BS / 4; ++c4) {
+                        const float4 wv = wrow[c4];
+                        const float4 xv = xv4[c4];
+                        t0 = fmaf(wv.x, xv.x, t0);
+                        t1 = fmaf(wv.y, xv.y, t1);
+                        t0 = fmaf(wv.z, xv.z, t0);
+                        t1 = fmaf(wv.w, xv.w, t1);
+                    }
+                    const float t = t0 + t1;
+                    q2 = fmaf(t, t, q2);
+                });
+                e2 = group_sum<BS>(e2);
+                q2 = group_sum<BS>(q2);
+                snum += -0.5f * e2;
+                sden += (p.den_mode == VMP_DEN_GAUSS) ? (scl[2] - 0.5f * q2)
+                                                      : (scl[2] - 0.5f * (scl[3] + (float)D) * log1pf(q2 / scl[3]));
+            }
+            // ---------------- per-pair results
+            if (gl == 0) {
+                kst[3 * k + 0] = score;
+                kst[3 * k + 1] = snum / (float)S + hld - 0.5f * (float)VMP_LOG_2PI * (float)D;
+                kst[3 * k + 2] = sden / (float)S;
+            }
+            // online Gumbel-max draw of z_n (tf.multinomial GPU algorithm): keep the running arg-max and its sample
+            const float u = p.gum_u != nullptr ? p.gum_u[pair] : philox_uniform_pair(p.seed, pair);
+            const float cand = score + gumbel_from_uniform<float>(u);
+            if (cand > best) {
+                best = cand;
+                zbest = k;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) xbest[r] = x0[r];
+            }
+        }
+
+        // ---------------- per-point epilogue: log-sum-exp over K, log_r, ELBO partials, selected sample
+        __syncwarp();
+        float mx = -CUDART_INF_F;
+        for (int k = gl; k < K; k += BS) mx = fmaxf(mx, kst[3 * k]);
+        mx = group_max<BS>(mx);
+        double se = 0.0;
+        for (int k = gl; k < K; k += BS) se += (double)expf(kst[3 * k] - mx);
+        se = group_sum_d<BS>(se);
+        const float lse = mx + (float)log(se);
+        double en = 0.0, ed = 0.0;
+        if (active) {
+            for (int k = gl; k < K; k += BS) {
+                const float lr = kst[3 * k] - lse;
+                p.log_r[n * K + k] = lr;
+                const double r = (double)expf(lr);
+                en += r * ((double)kst[3 * k + 1] + (double)lr);
+                ed += r * (double)kst[3 * k + 2];
+            }
+            if (p.x_sample != nullptr) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) p.x_sample[n * D + r * BS + gl] = xbest[r];
+            }
+            if (p.z != nullptr && gl == 0) p.z[n] = zbest;
+        }
+        en = group_sum_d<BS>(en);
+        ed = group_sum_d<BS>(ed);
+        if (gl == 0 && active) {
+            atomicAdd(&cta_acc[0], en);
+            atomicAdd(&cta_acc[1], ed);
+            if (bad) atomicAdd(&cta_acc[3], 1.0);
+        }
+        __syncthreads();   // stage buffers and kst are reused by the next tile
+    }
+    __syncthreads();
+    if (tid == 0) {
+        atomicAdd(p.elbo_acc + 0, cta_acc[0]);
+        atomicAdd(p.elbo_acc + 1, cta_acc[1]);
+        atomicAdd(p.elbo_acc + 2, cta_acc[0] - cta_acc[1]);
+        if (cta_acc[3] != 0.0) atomicAdd(p.elbo_acc + 3, cta_acc[3]);
+    }
+}
+
+template <int D> struct FastLaunch;
+template <> struct FastLaunch<64> { static constexpr int WARPS = 8, MINB = 1; };
+template <> struct FastLaunch<32> { static constexpr int WARPS = 8, MINB = 2; };
+template <> struct FastLaunch<16> { static constexpr int WARPS = 8, MINB = 2; };
+
+template <int D>
+size_t fast_smem_bytes(int K) {
+    using G = FastGeom<D>;
+    constexpr int PPC = FastLaunch<D>::WARPS * (32 / G::BS);
+    return sizeof(float) * (2 * (size_t)G::REC + (size_t)PPC * G::GS + (size_t)PPC * K * 3);
+}
+
+template <int D>
+int launch_fast(const FastParams& p0, bool use_tma, cudaStream_t st) {
+    using G = FastGeom<D>;
+    constexpr int WARPS = FastLaunch<D>::WARPS, MINB = FastLaunch<D>::MINB;
+    constexpr int PPC = WARPS * (32 / G::BS);
+    FastParams p = p0;
+    p.ntiles = (p.N + PPC - 1) / PPC;
+    const size_t smem = fast_smem_bytes<D>(p.K);
+    auto k1 = local_step_fast_kernel<D, WARPS, MINB, true>;
+    auto k0 = local_step_fast_kernel<D, WARPS, MINB, false>;
+    auto kern = use_tma ? k1 : k0;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)sms * occ;
+    if (grid > p.ntiles) grid = p.ntiles;
+    kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(p);
+    return launch_status();
+}
+
+}  // namespace vmp

@@ -160,17 +160,22 @@ def sample_x_per_comp(eta1, eta2, nb_samples, seed=0, *, noise=None):
     return (mean + nz).permute(0, 1, 3, 2).contiguous()
 
 
-def subsample_x(x_k_samples, log_q_z_given_y, seed=0, *, u=None):
-    """svae.py:122-151 : x_samples[n,s] = x_k_samples[n, z_ns, s], z_ns ~ Cat(softmax(log q)) by inverse CDF
-    (tf.multinomial's CPU algorithm, cdf in double).  u: uniforms[N,S]; default Philox keyed by `seed`."""
+def subsample_x(x_k_samples, log_q_z_given_y, seed=0, *, u=None, gumbel_u=None):
+    """svae.py:122-151 : x_samples[n,s] = x_k_samples[n, z_ns, s], z_ns ~ Cat(softmax(log q)) (tf.multinomial).
+    Default / gumbel_u[N,S,K]: Gumbel-max, z = argmax_k(log q - log(-log u)) (TF's GPU kernel; for s = 0 and the same
+    `seed` this is the draw the fused step makes).  u[N,S]: inverse-CDF search in double (TF's CPU kernel).
+    Stand-alone form of the gather for the reference's call order; the fused step selects inside the kernel."""
     N, K, S, L = x_k_samples.shape
     dev = x_k_samples.device
-    if u is None:
-        u = torch.stack([core.fill_noise(N, 1, 1, 1, seed + 7919 * s, x_k_samples.dtype, dev, want_noise=False)[1]
-                         for s in range(S)], dim=1)
-    lg = log_q_z_given_y.to(torch.float64)
-    cdf = torch.cumsum(torch.exp(lg - lg.max(dim=1, keepdim=True).values), dim=1)
-    z = torch.searchsorted(cdf, u.to(torch.float64) * cdf[:, -1:], right=True).clamp_(max=K - 1)
+    if u is not None:
+        lg = log_q_z_given_y.to(torch.float64)
+        cdf = torch.cumsum(torch.exp(lg - lg.max(dim=1, keepdim=True).values), dim=1)
+        z = torch.searchsorted(cdf, u.to(torch.float64) * cdf[:, -1:], right=True).clamp_(max=K - 1)
+    else:
+        if gumbel_u is None:
+            gumbel_u = torch.stack([core.fill_noise(N, K, 1, 1, seed + 7919 * s, x_k_samples.dtype, dev,
+                                                    want_noise=False)[1] for s in range(S)], dim=1)
+        z = torch.argmax(log_q_z_given_y.unsqueeze(1) - torch.log(-torch.log(gumbel_u)), dim=2)
     n_idx = torch.arange(N, device=dev).reshape(-1, 1).expand(N, S)
     s_idx = torch.arange(S, device=dev).reshape(1, -1).expand(N, S)
     return x_k_samples[n_idx, z, s_idx]

@@ -29,6 +29,7 @@ class SVAEStep(object):
         self.red = torch.zeros(K * slen + 4, dtype=torch.float64, device=self.device)
         self.stats = self.red[:K * slen].view(K, slen)
         self.elbo_acc = self.red[K * slen:]
+        self.workspace = core.local_step_workspace(K, D, self.device) if dtype == torch.float32 else None
         self.pg = process_group
         if use_dist is None:
             use_dist = torch.distributed.is_available() and torch.distributed.is_initialized() and \
@@ -50,7 +51,8 @@ class SVAEStep(object):
         if kernel_events is not None:       # CUDA events bracketing the dominant kernel (bench.py roofline)
             kernel_events[0].record()
         core.local_step(eta1, eta2_diag, self.phi_rec, self.theta_rec, self.S, den_mode=self.den_mode, noise=noise,
-                        u=u, seed=seed, log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc)
+                        u=u, seed=seed, log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc,
+                        workspace=self.workspace)
         if kernel_events is not None:
             kernel_events[1].record()
         core.suffstats(self.x_sample, self.log_r, r_is_log=True, stats=self.stats)
