@@ -229,7 +229,7 @@ static int try_fast(int64_t N, int K, int D, int S, const float* eta1, const flo
     const int minb = D == 64 ? 1 : 2;
     if (smem * minb > 220 * 1024) return -100;
     float* recs = static_cast<float*>(work);
-    pack_fast_records_kernel<<<K, 256, 0, st>>>(K, D, phi_rec, theta_rec, recs);
+    launch_pack_fast_records(K, D, phi_rec, theta_rec, recs, st);
     if (int e = launch_status()) return e;
     FastParams p{N, K, S, den_mode, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
     const bool tma = tma_enabled();

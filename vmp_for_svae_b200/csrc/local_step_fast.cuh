@@ -1,13 +1,15 @@
 // local_step_fast.cuh — the register-resident group engine of the fused local step (fp32, D in {16, 32, 64}).
 //
-// Mapping.  BS lanes of a warp ("group") own one (point n, component k) pair; lane gl owns rows r*BS + gl,
-// r < ROWS = D/BS, of the D x D system.  The lower triangle of P~ = P2_k + diag(p1_n) lives in registers
+// Mapping.  BS = D/4 lanes of a warp ("group") own one (point n, component k) pair; lane gl owns rows r*BS + gl,
+// r < ROWS = 4, of the D x D system.  The lower triangle of P~ = P2_k + diag(p1_n) lives in registers
 // (A[r][c], c < (r+1)*BS; entries right of the diagonal are don't-care slots that are computed but never feed a
 // meaningful value), so the whole factorisation runs out of the register file:
 //   * right-looking Cholesky: at step j the pivot is broadcast with one shuffle, every lane scales its own entries
 //     of column j, publishes them to a 2 x D shared-memory column buffer, and updates its rows with the column read
-//     back as 128-bit broadcasts (FMA : LDS.128 = 4*ROWS : 1);
-//   * the two forward substitutions a = L^-1 P2 d, a1 = L^-1 P1 d ride along as extra right-hand sides;
+//     back as 128-bit broadcasts.  The update is issued as packed FFMA2 (PTX fma.rn.f32x2, sm_100): two FMAs per
+//     instruction with the row's multiplier as broadcast scalar operand — measured 1.65x over scalar FFMA, which on
+//     this part cannot reach the FP32 peak (profiles/);
+//   * the two forward substitutions a = L^-1 P2 d, a1 = L^-1 P1 d ride along as a packed right-hand-side pair;
 //   * back substitution L^T y = eps - a goes block by block (BS x BS) with the blocks transposed through a padded
 //     shared-memory tile, the solved block broadcast through shared memory;
 //   * the theta quadratic form |W_k (x - m_k)|^2 is a row-owned triangular mat-vec against the staged W_k.
@@ -17,6 +19,8 @@
 // double-buffered stage, issued one component ahead.  Per point, the K scores / ELBO terms sit in shared memory until
 // the log-sum-exp; the categorical draw is an online Gumbel-max (tf.multinomial's GPU algorithm), so the selected
 // sample x[n, z_n, 0] is simply the running arg-max's sample and no second pass is needed.
+// Every loop whose bounds or register indices depend on an outer index is a compile-time static_for: the kernel
+// is straight-line code (~8k instructions per component at D=64) with the matrix held in ~160 named registers.
 #pragma once
 #include <type_traits>
 
@@ -52,42 +56,31 @@ template <int D> struct FastGeom {
     static constexpr int GS = ((GS_RAW - BS + 31) / 32) * 32 + BS;
 };
 
+template <int D> struct FastLaunch;
+template <> struct FastLaunch<64> { static constexpr int WARPS = 8, MINB = 1; };
+template <> struct FastLaunch<32> { static constexpr int WARPS = 8, MINB = 2; };
+template <> struct FastLaunch<16> { static constexpr int WARPS = 8, MINB = 2; };
+
 __host__ __device__ inline int fast_rec_len(int D) { return 2 * D * (D + 4) + 2 * D + 8; }
 
-// (phi_rec, theta_rec) of prepare.cu -> padded staged records
-__global__ void pack_fast_records_kernel(int K, int D, const float* __restrict__ phi_rec,
-                                         const float* __restrict__ theta_rec, float* __restrict__ out) {
-    const int k = blockIdx.x;
-    const int LD = D + 4, REC = fast_rec_len(D);
-    const float* pr = phi_rec + (size_t)k * phi_record_len(D);
-    const float* tr = theta_rec + (size_t)k * theta_record_len(D);
-    float* o = out + (size_t)k * REC;
-    for (int e = threadIdx.x; e < D * LD; e += blockDim.x) {
-        const int i = e / LD, c = e - i * LD;
-        o[e] = c < D ? pr[i * D + c] : 0.f;
-        o[D * LD + e] = c < D ? tr[i * D + c] : 0.f;
-    }
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        o[2 * D * LD + i] = pr[D * D + i];           // mu2
-        o[2 * D * LD + D + i] = tr[D * D + i];       // m_theta
-    }
-    if (threadIdx.x < 8) {
-        float v = 0.f;
-        if (threadIdx.x == 0) v = pr[D * D + 2 * D];        // log pi
-        if (threadIdx.x == 1) v = pr[D * D + 2 * D + 1];    // logdet P2
-        if (threadIdx.x == 2) v = tr[D * D + D];            // cden
-        if (threadIdx.x == 3) v = tr[D * D + D + 1];        // nu
-        o[2 * D * LD + 2 * D + threadIdx.x] = v;
-    }
+template <int D>
+inline size_t fast_smem_bytes(int K) {
+    using G = FastGeom<D>;
+    constexpr int PPC = FastLaunch<D>::WARPS * (32 / G::BS);
+    return sizeof(float) * (2 * (size_t)G::REC + (size_t)PPC * G::GS + (size_t)PPC * K * 3);
 }
 
+// defined in fast_d16.cu / fast_d32.cu / fast_d64.cu (one translation unit per D so they compile in parallel)
+template <int D> int launch_fast(const FastParams& p, bool use_tma, cudaStream_t st);
+void launch_pack_fast_records(int K, int D, const float* phi_rec, const float* theta_rec, float* out, cudaStream_t st);
+
+#ifdef VMP_FAST_IMPL
 // ---- mbarrier / bulk-copy primitives (inline PTX) ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -107,7 +100,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// compile-time loop: the index is a template constant, so every inner bound / register index that depends on it is
+// compile-time loops: the index is a template constant, so every inner bound / register index that depends on it is
 // a constant at instantiation time (a plain `#pragma unroll` nest leaves j-dependent inner loops rolled and pushes
 // the register-resident matrix into local memory)
 template <int I, int N, typename F> __device__ __forceinline__ void static_for(F&& f) {
@@ -121,6 +114,22 @@ template <int I, typename F> __device__ __forceinline__ void static_for_down(F&&
         f(std::integral_constant<int, I - 1>{});
         static_for_down<I - 1>(f);
     }
+}
+
+// packed FP32x2 FMA of sm_100 (SASS FFMA2): two FMAs per issue slot.
+// (d0, d1) += a * (b0, b1), a broadcast scalar (ptxas folds the duplicate into the scalar-operand form)
+__device__ __forceinline__ void ffma2_bcast(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2,%2};\n\tmov.b64 rb, {%3,%4};\n\tmov.b64 rc, {%0,%1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0,%1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
+}
+// (d0, d1) += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%0,%1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0,%1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
 template <int BS> __device__ __forceinline__ float group_sum(float v) {
@@ -248,15 +257,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 constexpr int r = decltype(rc)::value;
                 const float4* prow = reinterpret_cast<const float4*>(P2s + (r * BS + gl) * LD);
                 const float4* dv4 = reinterpret_cast<const float4*>(vec);
-                float s0 = 0.f, s1 = 0.f;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
                 for (int c4 = 0; c4 < D / 4; ++c4) {
                     const float4 pv = prow[c4];
                     const float4 dv = dv4[c4];
-                    s0 = fmaf(pv.x, dv.x, s0);
-                    s1 = fmaf(pv.y, dv.y, s1);
-                    s0 = fmaf(pv.z, dv.z, s0);
-                    s1 = fmaf(pv.w, dv.w, s1);
+                    ffma2(s0, s1, pv.x, pv.y, dv.x, dv.y);
+                    ffma2(s2, s3, pv.z, pv.w, dv.z, dv.w);
                     if (4 * c4 < (r + 1) * BS) {
                         A[r][4 * c4 + 0] = pv.x;
                         A[r][4 * c4 + 1] = pv.y;
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                         A[r][4 * c4 + 3] = pv.w;
                     }
                 }
-                g[r] = s0 + s1;
+                g[r] = (s0 + s1) + (s2 + s3);
             });
 
             // ---------------- phase 2: right-looking Cholesky with the two forward substitutions riding along
@@ -291,25 +298,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     if (r == rj) l = own ? piv * inv : l;
                     A[r][j] = l;
                     cw[r * BS + gl] = l;
-                    g[r] = fmaf(-l, yj, g[r]);
-                    g1[r] = fmaf(-l, y1j, g1[r]);
+                    ffma2_bcast(g[r], g1[r], -l, yj, y1j);
                 }
                 __syncwarp();
-                const float4* cr4 = reinterpret_cast<const float4*>(cw);
-#pragma unroll
-                for (int c4 = (j + 1) / 4; c4 < D / 4; ++c4) {
-                    const float4 cv = cr4[c4];
+                // trailing update A[r][c] -= L[r][j] * L[c][j], c > j, as packed pairs (c0, c0+1)
+                static_for<(j + 1) / 4, D / 4>([&](auto c4c) {
+                    constexpr int c4 = decltype(c4c)::value;
+                    const float4 cv = reinterpret_cast<const float4*>(cw)[c4];
                     const float cvv[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int c = 4 * c4 + e;
-                        if (c > j) {
+                    for (int h = 0; h < 2; ++h) {
+                        const int c0 = 4 * c4 + 2 * h;
+                        if (c0 > j) {
 #pragma unroll
                             for (int r = rj; r < ROWS; ++r)
-                                if (c < (r + 1) * BS) A[r][c] = fmaf(-A[r][j], cvv[e], A[r][c]);
+                                if (c0 < (r + 1) * BS)
+                                    ffma2_bcast(A[r][c0], A[r][c0 + 1], -A[r][j], cvv[2 * h], cvv[2 * h + 1]);
+                        } else if (c0 + 1 > j) {
+#pragma unroll
+                            for (int r = rj; r < ROWS; ++r)
+                                if (c0 + 1 < (r + 1) * BS) A[r][c0 + 1] = fmaf(-A[r][j], cvv[2 * h + 1], A[r][c0 + 1]);
                         }
                     }
-                }
+                });
             });
             const float hld = 0.5f * hl;                          // sum_i log L_ii
             const float score = scl[0] - 0.5f * q + 0.5f * scl[1] - hld;
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                         w[rb] = fmaf(-t, yi, w[rb]);
                     }
                     if constexpr (rb > 0) {
-                        ybf[gl] = y[rb];
+                        ybf[gl] = -y[rb];                               // negated: the block updates become pure FMAs
                         static_for<0, rb>([&](auto rb2c) {
                             constexpr int rb2 = decltype(rb2c)::value;
                             __syncwarp();
@@ -366,16 +377,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                                     make_float4(A[rb][rb2 * BS + 4 * q4], A[rb][rb2 * BS + 4 * q4 + 1],
                                                 A[rb][rb2 * BS + 4 * q4 + 2], A[rb][rb2 * BS + 4 * q4 + 3]);
                             __syncwarp();
-                            float acc = w[rb2];
+                            float acc0 = w[rb2], acc1 = 0.f;
 #pragma unroll
                             for (int i4 = 0; i4 < BS / 4; ++i4) {
                                 const float4 yv = reinterpret_cast<const float4*>(ybf)[i4];
-                                acc = fmaf(-tbf[(4 * i4 + 0) * TS + gl], yv.x, acc);
-                                acc = fmaf(-tbf[(4 * i4 + 1) * TS + gl], yv.y, acc);
-                                acc = fmaf(-tbf[(4 * i4 + 2) * TS + gl], yv.z, acc);
-                                acc = fmaf(-tbf[(4 * i4 + 3) * TS + gl], yv.w, acc);
+                                ffma2(acc0, acc1, tbf[(4 * i4 + 0) * TS + gl], tbf[(4 * i4 + 1) * TS + gl], yv.x, yv.y);
+                                ffma2(acc0, acc1, tbf[(4 * i4 + 2) * TS + gl], tbf[(4 * i4 + 3) * TS + gl], yv.z, yv.w);
                             }
-                            w[rb2] = acc;
+                            w[rb2] = acc0 + acc1;
                         });
                     }
                 });
@@ -398,17 +407,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     constexpr int r = decltype(rc)::value;
                     const float4* wrow = reinterpret_cast<const float4*>(Ws + (r * BS + gl) * LD);
                     const float4* xv4 = reinterpret_cast<const float4*>(vec);
-                    float t0 = 0.f, t1 = 0.f;
+                    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
                     for (int c4 = 0; c4 < (r + 1) * BS / 4; ++c4) {
                         const float4 wv = wrow[c4];
                         const float4 xv = xv4[c4];
-                        t0 = fmaf(wv.x, xv.x, t0);
-                        t1 = fmaf(wv.y, xv.y, t1);
-                        t0 = fmaf(wv.z, xv.z, t0);
-                        t1 = fmaf(wv.w, xv.w, t1);
+                        ffma2(t0, t1, wv.x, wv.y, xv.x, xv.y);
+                        ffma2(t2, t3, wv.z, wv.w, xv.z, xv.w);
                     }
-                    const float t = t0 + t1;
+                    const float t = (t0 + t1) + (t2 + t3);
                     q2 = fmaf(t, t, q2);
                 });
                 e2 = group_sum<BS>(e2);
@@ -476,29 +483,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     }
 }
 
-template <int D> struct FastLaunch;
-template <> struct FastLaunch<64> { static constexpr int WARPS = 8, MINB = 1; };
-template <> struct FastLaunch<32> { static constexpr int WARPS = 8, MINB = 2; };
-template <> struct FastLaunch<16> { static constexpr int WARPS = 8, MINB = 2; };
-
-template <int D>
-size_t fast_smem_bytes(int K) {
-    using G = FastGeom<D>;
-    constexpr int PPC = FastLaunch<D>::WARPS * (32 / G::BS);
-    return sizeof(float) * (2 * (size_t)G::REC + (size_t)PPC * G::GS + (size_t)PPC * K * 3);
-}
-
-template <int D>
-int launch_fast(const FastParams& p0, bool use_tma, cudaStream_t st) {
+template <int D, bool TMA>
+static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     using G = FastGeom<D>;
     constexpr int WARPS = FastLaunch<D>::WARPS, MINB = FastLaunch<D>::MINB;
     constexpr int PPC = WARPS * (32 / G::BS);
     FastParams p = p0;
     p.ntiles = (p.N + PPC - 1) / PPC;
     const size_t smem = fast_smem_bytes<D>(p.K);
-    auto k1 = local_step_fast_kernel<D, WARPS, MINB, true>;
-    auto k0 = local_step_fast_kernel<D, WARPS, MINB, false>;
-    auto kern = use_tma ? k1 : k0;
+    auto kern = local_step_fast_kernel<D, WARPS, MINB, TMA>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148, occ = 1;
@@ -511,5 +504,11 @@ int launch_fast(const FastParams& p0, bool use_tma, cudaStream_t st) {
     kern<<<(unsigned)grid, WARPS * 32, smem, st>>>(p);
     return launch_status();
 }
+
+#define VMP_FAST_INSTANTIATE(DD)                                                                  \
+    template <> int launch_fast<DD>(const FastParams& p, bool use_tma, cudaStream_t st) {          \
+        return use_tma ? launch_fast_t<DD, true>(p, st) : launch_fast_t<DD, false>(p, st);         \
+    }
+#endif  // VMP_FAST_IMPL
 
 }  // namespace vmp
