@@ -21,6 +21,7 @@ def main():
     ap.add_argument('--S', type=int, default=1)
     ap.add_argument('--variants', default='0,1,2,3,4,5,6,7')
     ap.add_argument('--reps', type=int, default=3)
+    ap.add_argument('--wide', default='0')
     a = ap.parse_args()
     dev = torch.device('cuda', 0)
     dt = torch.float32
@@ -35,6 +36,7 @@ def main():
     for v in a.variants.split(','):
         os.environ['VMP_FAST_VARIANT'] = v.replace('g', '')
         os.environ['VMP_FORCE_GENERIC'] = '1' if v == 'g' else '0'
+        os.environ['VMP_FAST_WIDE'] = '1' if v == 'w' else '0'
         out = core.local_step(eta1, eta2d, phi_rec, theta_rec, a.S, seed=5, workspace=ws)   # warm-up
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

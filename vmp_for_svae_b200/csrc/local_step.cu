@@ -225,7 +225,12 @@ static int try_fast(int64_t N, int K, int D, int S, const float* eta1, const flo
     if (!fast_enabled() || x_in != nullptr || work == nullptr) return -100;
     const size_t need = fast_workspace_bytes(K, D);
     if (need == 0 || work_bytes < need) return -100;
-    size_t smem = D == 64 ? fast_smem_bytes<64>(K) : D == 32 ? fast_smem_bytes<32>(K) : fast_smem_bytes<16>(K);
+    // lanes per pair: D/4 ("narrow", 4 rows per lane) or D/2 ("wide", 2 rows per lane: fewer registers, more warps)
+    const char* we = std::getenv("VMP_FAST_WIDE");
+    const bool wide = we ? we[0] == '1' : false;
+    size_t smem = D == 64 ? (wide ? fast_smem_bytes<64, 32>(K) : fast_smem_bytes<64, 16>(K))
+                : D == 32 ? (wide ? fast_smem_bytes<32, 16>(K) : fast_smem_bytes<32, 8>(K))
+                          : (wide ? fast_smem_bytes<16, 8>(K) : fast_smem_bytes<16, 4>(K));
     const int minb = D == 64 ? 1 : 2;
     if (smem * minb > 220 * 1024) return -100;
     float* recs = static_cast<float*>(work);
@@ -233,9 +238,9 @@ static int try_fast(int64_t N, int K, int D, int S, const float* eta1, const flo
     if (int e = launch_status()) return e;
     FastParams p{N, K, S, den_mode, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
     const bool tma = tma_enabled();
-    if (D == 64) return launch_fast<64>(p, tma, st);
-    if (D == 32) return launch_fast<32>(p, tma, st);
-    return launch_fast<16>(p, tma, st);
+    if (D == 64) return wide ? launch_fast<64, 32>(p, tma, st) : launch_fast<64, 16>(p, tma, st);
+    if (D == 32) return wide ? launch_fast<32, 16>(p, tma, st) : launch_fast<32, 8>(p, tma, st);
+    return wide ? launch_fast<16, 8>(p, tma, st) : launch_fast<16, 4>(p, tma, st);
 }
 template <typename T>
 static int try_fast_t(int64_t, int, int, int, const T*, const T*, const T*, const T*, int, const T*, const T*, uint64_t,

@@ -45,8 +45,9 @@ struct FastParams {
     int64_t ntiles;
 };
 
-template <int D> struct FastGeom {
-    static constexpr int BS = D / 4;                 // lanes per pair (ROWS = 4)
+template <int D, int BS_> struct FastGeom {
+    static constexpr int BS = BS_;                   // lanes per pair
+    static constexpr int ROWS = D / BS_;             // rows per lane
     static constexpr int LD = D + 4;                 // padded row stride of the staged matrices
     static constexpr int REC = 2 * D * LD + 2 * D + 8;
     static constexpr int TS = BS + 4;                // transpose tile stride
@@ -56,22 +57,25 @@ template <int D> struct FastGeom {
     static constexpr int GS = ((GS_RAW - BS + 31) / 32) * 32 + BS;
 };
 
-template <int D> struct FastLaunch;
-template <> struct FastLaunch<64> { static constexpr int WARPS = 8, MINB = 1; };
-template <> struct FastLaunch<32> { static constexpr int WARPS = 8, MINB = 2; };
-template <> struct FastLaunch<16> { static constexpr int WARPS = 8, MINB = 2; };
+template <int D, int BS> struct FastLaunch;
+template <> struct FastLaunch<64, 16> { static constexpr int WARPS = 8, MINB = 1; };
+template <> struct FastLaunch<64, 32> { static constexpr int WARPS = 12, MINB = 1; };
+template <> struct FastLaunch<32, 8> { static constexpr int WARPS = 8, MINB = 2; };
+template <> struct FastLaunch<32, 16> { static constexpr int WARPS = 8, MINB = 2; };
+template <> struct FastLaunch<16, 4> { static constexpr int WARPS = 8, MINB = 2; };
+template <> struct FastLaunch<16, 8> { static constexpr int WARPS = 8, MINB = 2; };
 
 __host__ __device__ inline int fast_rec_len(int D) { return 2 * D * (D + 4) + 2 * D + 8; }
 
-template <int D>
+template <int D, int BS>
 inline size_t fast_smem_bytes(int K) {
-    using G = FastGeom<D>;
-    constexpr int PPC = FastLaunch<D>::WARPS * (32 / G::BS);
+    using G = FastGeom<D, BS>;
+    constexpr int PPC = FastLaunch<D, BS>::WARPS * (32 / G::BS);
     return sizeof(float) * (2 * (size_t)G::REC + (size_t)PPC * G::GS + (size_t)PPC * K * 3);
 }
 
 // defined in fast_d16.cu / fast_d32.cu / fast_d64.cu (one translation unit per D so they compile in parallel)
-template <int D> int launch_fast(const FastParams& p, bool use_tma, cudaStream_t st);
+template <int D, int BS> int launch_fast(const FastParams& p, bool use_tma, cudaStream_t st);
 void launch_pack_fast_records(int K, int D, const float* phi_rec, const float* theta_rec, float* out, cudaStream_t st);
 
 #ifdef VMP_FAST_IMPL
@@ -148,13 +152,13 @@ template <int BS> __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-template <int D, int WARPS, int MINB, bool TMA>
+template <int D, int BS, int WARPS, int MINB, bool TMA>
 __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const FastParams p) {
-    using G = FastGeom<D>;
-    constexpr int BS = G::BS, ROWS = 4, GPW = 32 / BS, PPC = WARPS * GPW, LD = G::LD, REC = G::REC, TS = G::TS;
+    using G = FastGeom<D, BS>;
+    constexpr int ROWS = G::ROWS, GPW = 32 / BS, PPC = WARPS * GPW, LD = G::LD, REC = G::REC, TS = G::TS;
     constexpr int GS = G::GS;
     constexpr unsigned FULL = 0xffffffffu;
-    static_assert(D % 16 == 0 && BS * ROWS == D, "D must be 16, 32 or 64");
+    static_assert(D % 16 == 0 && BS * ROWS == D && BS % 4 == 0 && 32 % BS == 0, "unsupported (D, BS)");
 
     extern __shared__ __align__(128) unsigned char smraw[];
     float* stage = reinterpret_cast<float*>(smraw);              // [2][REC]
@@ -483,15 +487,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     }
 }
 
-template <int D, bool TMA>
+template <int D, int BS, bool TMA>
 static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
-    using G = FastGeom<D>;
-    constexpr int WARPS = FastLaunch<D>::WARPS, MINB = FastLaunch<D>::MINB;
+    using G = FastGeom<D, BS>;
+    constexpr int WARPS = FastLaunch<D, BS>::WARPS, MINB = FastLaunch<D, BS>::MINB;
     constexpr int PPC = WARPS * (32 / G::BS);
     FastParams p = p0;
     p.ntiles = (p.N + PPC - 1) / PPC;
-    const size_t smem = fast_smem_bytes<D>(p.K);
-    auto kern = local_step_fast_kernel<D, WARPS, MINB, TMA>;
+    const size_t smem = fast_smem_bytes<D, BS>(p.K);
+    auto kern = local_step_fast_kernel<D, BS, WARPS, MINB, TMA>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148, occ = 1;
@@ -505,9 +509,9 @@ static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     return launch_status();
 }
 
-#define VMP_FAST_INSTANTIATE(DD)                                                                  \
-    template <> int launch_fast<DD>(const FastParams& p, bool use_tma, cudaStream_t st) {          \
-        return use_tma ? launch_fast_t<DD, true>(p, st) : launch_fast_t<DD, false>(p, st);         \
+#define VMP_FAST_INSTANTIATE(DD, BB)                                                                \
+    template <> int launch_fast<DD, BB>(const FastParams& p, bool use_tma, cudaStream_t st) {      \
+        return use_tma ? launch_fast_t<DD, BB, true>(p, st) : launch_fast_t<DD, BB, false>(p, st); \
     }
 #endif  // VMP_FAST_IMPL
 
