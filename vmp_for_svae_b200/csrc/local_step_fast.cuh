@@ -51,9 +51,10 @@ template <int D, int BS_> struct FastGeom {
     static constexpr int LD = D + 4;                 // padded row stride of the staged matrices
     static constexpr int REC = 2 * D * LD + 2 * D + 8;
     static constexpr int TS = BS + 4;                // transpose tile stride
-    // group scratch: col[2][D] | vec[D] | ybf[max(BS,4)] | tbf[BS][TS]; kept congruent to BS mod 32 so the groups
-    // of one warp land in different banks
-    static constexpr int GS_RAW = 3 * D + (BS < 4 ? 4 : BS) + BS * TS;
+    // group scratch: col[2][D] | vec[D] | ybf[max(BS,4)] | tbf[BS][TS] | mub[D] | p1b[D] | xb[D]; kept congruent to BS
+    // mod 32 so the groups of one warp land in different banks.  mub / p1b / xb hold per-point state (mu1, p1, the
+    // running arg-max sample) that would otherwise pin 12 registers across the whole factorisation.
+    static constexpr int GS_RAW = 6 * D + (BS < 4 ? 4 : BS) + BS * TS;
     static constexpr int GS = ((GS_RAW - BS + 31) / 32) * 32 + BS;
 };
 
@@ -136,6 +137,12 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int BS> __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
     for (int o = BS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, BS);
@@ -174,6 +181,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     float* vec = col + 2 * D;             // [D]
     float* ybf = vec + D;                 // [BS]
     float* tbf = ybf + (BS < 4 ? 4 : BS); // [BS][TS]
+    float* mub = tbf + BS * TS;           // [D] mu1 of this group's point
+    float* p1b = mub + D;                 // [D] p1
+    float* xb = p1b + D;                  // [D] sample of the running Gumbel arg-max
     float* kst = ksm + (size_t)grp * p.K * 3;
     const int K = p.K, S = p.S;
 
@@ -211,13 +221,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
         const bool active = n_raw < p.N;
         const int64_t n = active ? n_raw : p.N - 1;
 
-        float p1[ROWS], mu1[ROWS], xbest[ROWS];
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
             const int row = r * BS + gl;
-            p1[r] = -2.f * p.eta2d[n * D + row];
-            mu1[r] = p.eta1[n * D + row] / p1[r];
-            xbest[r] = 0.f;
+            const float p1v = -2.f * p.eta2d[n * D + row];
+            p1b[row] = p1v;
+            mub[row] = p.eta1[n * D + row] / p1v;
+            xb[row] = 0.f;
         }
         float best = -CUDART_INF_F;
         int zbest = 0;
@@ -250,8 +260,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 const int row = r * BS + gl;
-                const float d = mu1[r] - mu2[row];
-                g1[r] = p1[r] * d;
+                const float d = mub[row] - mu2[row];
+                g1[r] = p1b[row] * d;
                 vec[row] = d;
                 a[r] = 0.f;
                 idg[r] = 0.f;
@@ -276,6 +286,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     }
                 }
                 g[r] = (s0 + s1) + (s2 + s3);
+                // P~ = P2 + diag(p1): the diagonal entry of this lane's row sits in column r*BS + gl
+                const float p1r = p1b[r * BS + gl];
+#pragma unroll
+                for (int cc = 0; cc < BS; ++cc) A[r][r * BS + cc] += (gl == cc) ? p1r : 0.f;
             });
 
             // ---------------- phase 2: right-looking Cholesky with the two forward substitutions riding along
@@ -283,12 +297,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             static_for<0, D>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 constexpr int rj = j / BS, lj = j % BS;
-                const float piv = __shfl_sync(FULL, A[rj][j] + p1[rj], lj, BS);
+                const float piv = __shfl_sync(FULL, A[rj][j], lj, BS);
                 bad |= !(piv > 0.f);
-                float inv = rsqrtf(piv);
+                float inv = rsqrt_approx(piv);                           // bare MUFU.RSQ (pivots are O(1): no denormals)
                 inv = inv * fmaf(-0.5f * piv * inv, inv, 1.5f);          // one Newton step: ~0.5 ulp
                 pprod *= piv;
-                if ((j & 3) == 3) { hl += logf(pprod); pprod = 1.f; }
+                if ((j & 3) == 3) { hl += logf(pprod); pprod = 1.f; }   // log of 4 pivots at a time (no overflow up to 1e9 each)
                 const float yj = __shfl_sync(FULL, g[rj] * inv, lj, BS);
                 const float y1j = __shfl_sync(FULL, g1[rj] * inv, lj, BS);
                 q = fmaf(yj, y1j, q);
@@ -306,9 +320,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 }
                 __syncwarp();
                 // trailing update A[r][c] -= L[r][j] * L[c][j], c > j, as packed pairs (c0, c0+1)
-                static_for<(j + 1) / 4, D / 4>([&](auto c4c) {
+                // the 128-bit broadcast reads are software-pipelined PF chunks ahead of their FFMA2s (ptxas otherwise
+                // recycles one 4-register buffer and exposes the shared-memory latency on every chunk)
+                constexpr int C4B = (j + 1) / 4, C4E = D / 4, PF = 3;
+                const float4* cr4 = reinterpret_cast<const float4*>(cw);
+                float4 pf[PF];
+#pragma unroll
+                for (int t = 0; t < PF; ++t)
+                    if (C4B + t < C4E) pf[t] = cr4[C4B + t];
+                static_for<C4B, C4E>([&](auto c4c) {
                     constexpr int c4 = decltype(c4c)::value;
-                    const float4 cv = reinterpret_cast<const float4*>(cw)[c4];
+                    const float4 cv = pf[(c4 - C4B) % PF];
+                    if constexpr (c4 + PF < C4E) pf[(c4 - C4B) % PF] = cr4[c4 + PF];
                     const float cvv[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -397,7 +420,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 __syncwarp();
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
-                    x[r] = mu1[r] + y[r];
+                    x[r] = mub[r * BS + gl] + y[r];
                     vec[r * BS + gl] = x[r] - mth[r * BS + gl];
                     if (s == 0) x0[r] = x[r];
                 }
@@ -441,7 +464,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 best = cand;
                 zbest = k;
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) xbest[r] = x0[r];
+                for (int r = 0; r < ROWS; ++r) xb[r * BS + gl] = x0[r];
             }
         }
 
@@ -465,7 +488,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             }
             if (p.x_sample != nullptr) {
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) p.x_sample[n * D + r * BS + gl] = xbest[r];
+                for (int r = 0; r < ROWS; ++r) p.x_sample[n * D + r * BS + gl] = xb[r * BS + gl];
             }
             if (p.z != nullptr && gl == 0) p.z[n] = zbest;
         }

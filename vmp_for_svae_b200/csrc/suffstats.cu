@@ -15,6 +15,20 @@ namespace vmp {
 constexpr int SS_CH = 64;      // points per shared-memory chunk
 constexpr int SS_KT = 2;       // components per thread
 
+// (d0, d1) += a * (b0, b1): packed FFMA2 for float (two FMAs per issue slot on sm_100), plain FMAs for double
+__device__ __forceinline__ void fma2_bcast(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2,%2};\n\tmov.b64 rb, {%3,%4};\n\tmov.b64 rc, {%0,%1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0,%1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2_bcast(double& d0, double& d1, double a, double b0, double b1) {
+    d0 = fma(a, b0, d0);
+    d1 = fma(a, b1, d1);
+}
+
+// Thread t of a k-group owns the 4x4 block (bi, bj), bi >= bj, of the symmetric (D+1) x (D+1) matrix
+// sum_n w_nk xt xt^T, xt = [x, 1] (lower block triangle only: the statistic is symmetric), for KT components.
 template <typename T>
 __global__ void __launch_bounds__(320)
 suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per_slice, const T* __restrict__ x,
@@ -29,8 +43,12 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
     const int64_t n_end = min(N, n_begin + pts_per_slice);
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
-    const int g = tid / (nb * nb), b = tid - g * nb * nb;
-    const int bi = b / nb, bj = b - bi * nb;
+    const int nt = nb * (nb + 1) / 2;
+    const int g = tid / nt, b = tid - g * nt;
+    int bi = (int)((sqrtf(8.f * (float)b + 1.f) - 1.f) * 0.5f);
+    while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+    while (bi * (bi + 1) / 2 > b) --bi;
+    const int bj = b - bi * (bi + 1) / 2;
     const bool active = g < G && (k0 + g * SS_KT) < K;
 
     T acc[4][4][SS_KT];
@@ -76,12 +94,12 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
 #pragma unroll
                 for (int q = 0; q < SS_KT; ++q) w[q] = ws[(size_t)p * KC + g * SS_KT + q];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int q = 0; q < SS_KT; ++q)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const T pij = xi[i] * xj[j];
-#pragma unroll
-                        for (int q = 0; q < SS_KT; ++q) acc[i][j][q] = fma(w[q], pij, acc[i][j][q]);
+                    for (int i = 0; i < 4; ++i) {
+                        const T wx = w[q] * xi[i];
+                        fma2_bcast(acc[i][0][q], acc[i][1][q], wx, xj[0], xj[1]);
+                        fma2_bcast(acc[i][2][q], acc[i][3][q], wx, xj[2], xj[3]);
                     }
                 if (u_nk != nullptr && b == 0) {
 #pragma unroll
@@ -111,9 +129,14 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
             for (int j = 0; j < 4; ++j) {
                 const int gi = bi * 4 + i, gj = bj * 4 + j;
                 const double v = dacc[i][j][q];
-                if (gi < D && gj < D) atomicAdd(out + 2 + D + gi * D + gj, v);
-                else if (gi < D && gj == D) atomicAdd(out + 2 + gi, v);
-                else if (gi == D && gj == D) {
+                if (gi < D && gj < D) {
+                    if (gi >= gj) {                      // lower triangle only, mirrored: the statistic is exactly symmetric
+                        atomicAdd(out + 2 + D + gi * D + gj, v);
+                        if (gi != gj) atomicAdd(out + 2 + D + gj * D + gi, v);
+                    }
+                } else if (gi == D && gj < D) {
+                    atomicAdd(out + 2 + gj, v);                                  // row of the augmented 1: sum w x
+                } else if (gi == D && gj == D) {
                     atomicAdd(out + 1, v);
                     if (u_nk == nullptr) atomicAdd(out + 0, v);
                 }
@@ -125,19 +148,21 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
 template <typename T>
 int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
               void* stream) {
-    if (N < 0 || K <= 0 || !x || !r || !stats) return VMP_E_BADARG;
+    if (N < 0 || K <= 0) return VMP_E_BADARG;
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     if (N == 0) return VMP_OK;
+    if (!x || !r || !stats) return VMP_E_BADARG;
     const int D4 = ((D + 1 + 3) / 4) * 4;
     const int nb = D4 / 4;
-    int G = 256 / (nb * nb);
+    const int nt = nb * (nb + 1) / 2;
+    int G = 256 / nt;
     if (G < 1) G = 1;
     const int kgroups = (K + SS_KT - 1) / SS_KT;
     if (G > kgroups) G = kgroups;
-    const int threads = ((nb * nb * G + 31) / 32) * 32;
+    const int threads = ((nt * G + 31) / 32) * 32;
     const int KC = SS_KT * G;
     const int ktiles = (K + KC - 1) / KC;
-    int nslices = (2 * 148 + ktiles - 1) / ktiles;
+    int nslices = (4 * 148 + ktiles - 1) / ktiles;
     const int64_t min_slice = 4 * SS_CH;
     if ((int64_t)nslices * min_slice > N) nslices = (int)((N + min_slice - 1) / min_slice);
     if (nslices < 1) nslices = 1;
