@@ -51,10 +51,10 @@ template <int D, int BS_> struct FastGeom {
     static constexpr int LD = D + 4;                 // padded row stride of the staged matrices
     static constexpr int REC = 2 * D * LD + 2 * D + 8;
     static constexpr int TS = BS + 4;                // transpose tile stride
-    // group scratch: col[2][D] | vec[D] | ybf[max(BS,4)] | tbf[BS][TS] | mub[D] | p1b[D] | xb[D]; kept congruent to BS
+    // group scratch: col[2][D] | vec[D] | ybf[max(BS,4)] | tbf[BS][TS] | mub[D] | p1b[D] | xb[D] | ab[D] | ib[D]; kept congruent to BS
     // mod 32 so the groups of one warp land in different banks.  mub / p1b / xb hold per-point state (mu1, p1, the
     // running arg-max sample) that would otherwise pin 12 registers across the whole factorisation.
-    static constexpr int GS_RAW = 6 * D + (BS < 4 ? 4 : BS) + BS * TS;
+    static constexpr int GS_RAW = 8 * D + (BS < 4 ? 4 : BS) + BS * TS;
     static constexpr int GS = ((GS_RAW - BS + 31) / 32) * 32 + BS;
 };
 
@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     float* mub = tbf + BS * TS;           // [D] mu1 of this group's point
     float* p1b = mub + D;                 // [D] p1
     float* xb = p1b + D;                  // [D] sample of the running Gumbel arg-max
+    float* ab = xb + D;                   // [D] a = L^-1 P2 d of the current pair
+    float* ib = ab + D;                   // [D] 1 / L_jj of the current pair
     float* kst = ksm + (size_t)grp * p.K * 3;
     const int K = p.K, S = p.S;
 
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             const float* scl = mth + D;
 
             // ---------------- phase 1: d, g1 = P1 d, g = P2 d, A <- P2 rows
-            float g[ROWS], g1[ROWS], a[ROWS], idg[ROWS];
+            float g[ROWS], g1[ROWS];
             float A[ROWS][D];
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
@@ -263,8 +265,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 const float d = mub[row] - mu2[row];
                 g1[r] = p1b[row] * d;
                 vec[row] = d;
-                a[r] = 0.f;
-                idg[r] = 0.f;
             }
             __syncwarp();
             static_for<0, ROWS>([&](auto rc) {
@@ -307,8 +307,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 const float y1j = __shfl_sync(FULL, g1[rj] * inv, lj, BS);
                 q = fmaf(yj, y1j, q);
                 const bool own = (gl == lj);
-                a[rj] = own ? yj : a[rj];
-                idg[rj] = own ? inv : idg[rj];
+                if (own) { ab[j] = yj; ib[j] = inv; }                    // kept in smem: frees 8 registers
                 float* cw = col + (j & 1) * D;
 #pragma unroll
                 for (int r = rj; r < ROWS; ++r) {
@@ -322,7 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 // trailing update A[r][c] -= L[r][j] * L[c][j], c > j, as packed pairs (c0, c0+1)
                 // the 128-bit broadcast reads are software-pipelined PF chunks ahead of their FFMA2s (ptxas otherwise
                 // recycles one 4-register buffer and exposes the shared-memory latency on every chunk)
-                constexpr int C4B = (j + 1) / 4, C4E = D / 4, PF = 3;
+                constexpr int C4B = (j + 1) / 4, C4E = D / 4, PF = 4;
                 const float4* cr4 = reinterpret_cast<const float4*>(cw);
                 float4 pf[PF];
 #pragma unroll
@@ -357,7 +356,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             float snum = 0.f, sden = 0.f;
             float x0[ROWS];
             for (int s = 0; s < S; ++s) {
-                float w[ROWS], y[ROWS];
+                float w[ROWS], y[ROWS], idg[ROWS];
                 if (p.noise != nullptr) {
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r) w[r] = p.noise[(pair * D + r * BS + gl) * (uint64_t)S + s];
@@ -373,8 +372,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
                     e2 = fmaf(w[r], w[r], e2);
-                    w[r] -= a[r];
+                    w[r] -= ab[r * BS + gl];
                     y[r] = 0.f;
+                    idg[r] = ib[r * BS + gl];
                 }
                 // back substitution, block rows from the bottom
                 static_for_down<ROWS>([&](auto rbc) {
