@@ -37,6 +37,7 @@ def main():
         os.environ['VMP_FAST_VARIANT'] = v.replace('g', '')
         os.environ['VMP_FORCE_GENERIC'] = '1' if v == 'g' else '0'
         os.environ['VMP_FAST_WIDE'] = '1' if v == 'w' else '0'
+        os.environ['VMP_FAST_PF'] = v[2:] if v.startswith('pf') else '4'
         out = core.local_step(eta1, eta2d, phi_rec, theta_rec, a.S, seed=5, workspace=ws)   # warm-up
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -22,6 +22,7 @@
 // Every loop whose bounds or register indices depend on an outer index is a compile-time static_for: the kernel
 // is straight-line code (~8k instructions per component at D=64) with the matrix held in ~160 named registers.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -159,7 +160,7 @@ template <int BS> __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-template <int D, int BS, int WARPS, int MINB, bool TMA>
+template <int D, int BS, int WARPS, int MINB, bool TMA, int PF>
 __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const FastParams p) {
     using G = FastGeom<D, BS>;
     constexpr int ROWS = G::ROWS, GPW = 32 / BS, PPC = WARPS * GPW, LD = G::LD, REC = G::REC, TS = G::TS;
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 // trailing update A[r][c] -= L[r][j] * L[c][j], c > j, as packed pairs (c0, c0+1)
                 // the 128-bit broadcast reads are software-pipelined PF chunks ahead of their FFMA2s (ptxas otherwise
                 // recycles one 4-register buffer and exposes the shared-memory latency on every chunk)
-                constexpr int C4B = (j + 1) / 4, C4E = D / 4, PF = 4;
+                constexpr int C4B = (j + 1) / 4, C4E = D / 4;
                 const float4* cr4 = reinterpret_cast<const float4*>(cw);
                 float4 pf[PF];
 #pragma unroll
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     }
 }
 
-template <int D, int BS, bool TMA>
+template <int D, int BS, bool TMA, int PF>
 static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     using G = FastGeom<D, BS>;
     constexpr int WARPS = FastLaunch<D, BS>::WARPS, MINB = FastLaunch<D, BS>::MINB;
@@ -518,7 +519,7 @@ static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     FastParams p = p0;
     p.ntiles = (p.N + PPC - 1) / PPC;
     const size_t smem = fast_smem_bytes<D, BS>(p.K);
-    auto kern = local_step_fast_kernel<D, BS, WARPS, MINB, TMA>;
+    auto kern = local_step_fast_kernel<D, BS, WARPS, MINB, TMA, PF>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148, occ = 1;
@@ -532,9 +533,23 @@ static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     return launch_status();
 }
 
+// prefetch depth of the column-chunk loads (tuning knob VMP_FAST_PF, only compiled in for the D=64 narrow engine)
+template <int D, int BS>
+static int launch_fast_pick(const FastParams& p, bool use_tma, cudaStream_t st) {
+    if (!use_tma) return launch_fast_t<D, BS, false, 4>(p, st);
+#ifdef VMP_FAST_PF_VARIANTS
+    const char* e = std::getenv("VMP_FAST_PF");
+    const int pf = e ? std::atoi(e) : 4;
+    if (pf == 2) return launch_fast_t<D, BS, true, 2>(p, st);
+    if (pf == 6) return launch_fast_t<D, BS, true, 6>(p, st);
+    if (pf == 8) return launch_fast_t<D, BS, true, 8>(p, st);
+#endif
+    return launch_fast_t<D, BS, true, 4>(p, st);
+}
+
 #define VMP_FAST_INSTANTIATE(DD, BB)                                                                \
     template <> int launch_fast<DD, BB>(const FastParams& p, bool use_tma, cudaStream_t st) {      \
-        return use_tma ? launch_fast_t<DD, BB, true>(p, st) : launch_fast_t<DD, BB, false>(p, st); \
+        return launch_fast_pick<DD, BB>(p, use_tma, st);                                           \
     }
 #endif  // VMP_FAST_IMPL
 
