@@ -213,6 +213,9 @@ def run_cuda(args):
     h2d = 2 * n_per_gpu * D * 4
     d2h = 4 * 8 + K * 4
 
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     if rank != 0:
         return 0
     total_points = n_per_gpu * world
