@@ -26,18 +26,28 @@ __device__ __forceinline__ void fma2_bcast(double& d0, double& d1, double a, dou
     d0 = fma(a, b0, d0);
     d1 = fma(a, b1, d1);
 }
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
 
 // Thread t of a k-group owns the 4x4 block (bi, bj), bi >= bj, of the symmetric (D+1) x (D+1) matrix
 // sum_n w_nk xt xt^T, xt = [x, 1] (lower block triangle only: the statistic is symmetric), for KT components.
+// Chunks of SS_CH points stream through a double-buffered shared-memory stage filled by cp.async one chunk ahead;
+// the augmented column [1, 0, ..] of the stage is written once and never overwritten.
 template <typename T>
 __global__ void __launch_bounds__(320)
 suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per_slice, const T* __restrict__ x,
                  const T* __restrict__ r, int r_is_log, const T* __restrict__ u_nk, double* __restrict__ stats) {
-    extern __shared__ unsigned char smraw[];
-    T* xs = reinterpret_cast<T*>(smraw);            // [SS_CH][D4]   xt = [x, 1, 0 pad]
-    T* ws = xs + (size_t)SS_CH * D4;                // [SS_CH][KC]   weights w
+    extern __shared__ __align__(16) unsigned char smraw[];
     const int KC = SS_KT * G;                       // components covered by this CTA
-    T* rs = ws + (size_t)SS_CH * KC;                // [SS_CH][KC]   r (only when u_nk != nullptr)
+    T* xs0 = reinterpret_cast<T*>(smraw);           // [2][SS_CH][D4]   xt = [x, 1, 0 pad]
+    T* ws0 = xs0 + 2 * (size_t)SS_CH * D4;          // [2][SS_CH][KC]   weights w (raw r / log r until converted)
+    T* us0 = ws0 + 2 * (size_t)SS_CH * KC;          // [2][SS_CH][KC]   u (SMM) -> r after conversion
     const int k0 = blockIdx.x * KC;
     const int64_t n_begin = (int64_t)blockIdx.y * pts_per_slice;
     const int64_t n_end = min(N, n_begin + pts_per_slice);
@@ -50,6 +60,7 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
     while (bi * (bi + 1) / 2 > b) --bi;
     const int bj = b - bi * (bi + 1) / 2;
     const bool active = g < G && (k0 + g * SS_KT) < K;
+    const bool vec16 = (D % 4 == 0) && sizeof(T) == 4;
 
     T acc[4][4][SS_KT];
     double dacc[4][4][SS_KT];
@@ -64,25 +75,70 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
 #pragma unroll
     for (int q = 0; q < SS_KT; ++q) { racc[q] = T(0); dracc[q] = 0.0; }
 
-    for (int64_t c0 = n_begin; c0 < n_end; c0 += SS_CH) {
+    // augmented / padding columns of both stage buffers
+    for (int e = tid; e < 2 * SS_CH * (D4 - D); e += nthreads) {
+        const int p = e / (D4 - D), i = D + e % (D4 - D);
+        xs0[(size_t)p * D4 + i] = (i == D) ? T(1) : T(0);
+    }
+
+    auto prefetch = [&](int64_t c0, int buf) {
         const int cn = (int)min((int64_t)SS_CH, n_end - c0);
-        __syncthreads();
-        for (int e = tid; e < SS_CH * D4; e += nthreads) {
-            const int p = e / D4, i = e - p * D4;
-            T v = T(0);
-            if (p < cn) v = i < D ? x[(c0 + p) * D + i] : (i == D ? T(1) : T(0));
-            xs[e] = v;
+        T* xs = xs0 + (size_t)buf * SS_CH * D4;
+        T* ws = ws0 + (size_t)buf * SS_CH * KC;
+        T* us = us0 + (size_t)buf * SS_CH * KC;
+        if (vec16) {
+            const int per_row = D / 4;
+            for (int e = tid; e < cn * per_row; e += nthreads) {
+                const int p = e / per_row, q4 = e - p * per_row;
+                cp_async16(xs + (size_t)p * D4 + 4 * q4, x + (c0 + p) * D + 4 * q4);
+            }
+        } else {
+            for (int e = tid; e < cn * D; e += nthreads) {
+                const int p = e / D, i = e - p * D;
+                xs[(size_t)p * D4 + i] = x[(c0 + p) * D + i];
+            }
         }
-        for (int e = tid; e < SS_CH * KC; e += nthreads) {
+        for (int e = tid; e < cn * KC; e += nthreads) {
             const int p = e / KC, kk = e - p * KC;
-            T w = T(0), rv = T(0);
-            if (p < cn && k0 + kk < K) {
-                rv = r[(c0 + p) * K + k0 + kk];
+            if (k0 + kk < K) {
+                if (sizeof(T) == 4) {
+                    cp_async4(ws + e, r + (c0 + p) * K + k0 + kk);
+                    if (u_nk != nullptr) cp_async4(us + e, u_nk + (c0 + p) * K + k0 + kk);
+                } else {
+                    ws[e] = r[(c0 + p) * K + k0 + kk];
+                    if (u_nk != nullptr) us[e] = u_nk[(c0 + p) * K + k0 + kk];
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    int it = 0;
+    if (n_begin < n_end) prefetch(n_begin, 0);
+    for (int64_t c0 = n_begin; c0 < n_end; c0 += SS_CH, ++it) {
+        const int buf = it & 1;
+        const int cn = (int)min((int64_t)SS_CH, n_end - c0);
+        if (c0 + SS_CH < n_end) {
+            prefetch(c0 + SS_CH, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        T* xs = xs0 + (size_t)buf * SS_CH * D4;
+        T* ws = ws0 + (size_t)buf * SS_CH * KC;
+        T* us = us0 + (size_t)buf * SS_CH * KC;
+        // convert the weight tile in place: w = r (or exp(log r)) [* u], us <- r
+        for (int e = tid; e < cn * KC; e += nthreads) {
+            const int kk = e % KC;
+            T rv = T(0), w = T(0);
+            if (k0 + kk < K) {
+                rv = ws[e];
                 if (r_is_log) rv = t_exp(rv);
-                w = u_nk != nullptr ? rv * u_nk[(c0 + p) * K + k0 + kk] : rv;
+                w = u_nk != nullptr ? rv * us[e] : rv;
             }
             ws[e] = w;
-            if (u_nk != nullptr) rs[e] = rv;
+            if (u_nk != nullptr) us[e] = rv;
         }
         __syncthreads();
         if (active) {
@@ -103,7 +159,7 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
                     }
                 if (u_nk != nullptr && b == 0) {
 #pragma unroll
-                    for (int q = 0; q < SS_KT; ++q) racc[q] += rs[(size_t)p * KC + g * SS_KT + q];
+                    for (int q = 0; q < SS_KT; ++q) racc[q] += us[(size_t)p * KC + g * SS_KT + q];
                 }
             }
 #pragma unroll
@@ -115,6 +171,7 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
 #pragma unroll
             for (int q = 0; q < SS_KT; ++q) { dracc[q] += (double)racc[q]; racc[q] = T(0); }
         }
+        __syncthreads();      // everyone is done with this buffer before the next-but-one prefetch overwrites it
     }
     if (!active) return;
     const int SL = stats_len(D);
@@ -162,14 +219,14 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
     const int threads = ((nt * G + 31) / 32) * 32;
     const int KC = SS_KT * G;
     const int ktiles = (K + KC - 1) / KC;
-    int nslices = (4 * 148 + ktiles - 1) / ktiles;
+    int nslices = (6 * 148 + ktiles - 1) / ktiles;
     const int64_t min_slice = 4 * SS_CH;
     if ((int64_t)nslices * min_slice > N) nslices = (int)((N + min_slice - 1) / min_slice);
     if (nslices < 1) nslices = 1;
     int64_t pps = (N + nslices - 1) / nslices;
     pps = ((pps + SS_CH - 1) / SS_CH) * SS_CH;
     nslices = (int)((N + pps - 1) / pps);
-    const size_t smem = sizeof(T) * ((size_t)SS_CH * D4 + 2 * (size_t)SS_CH * KC);
+    const size_t smem = sizeof(T) * 2 * ((size_t)SS_CH * D4 + 2 * (size_t)SS_CH * KC);
     auto kern = suffstats_kernel<T>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
