@@ -105,7 +105,7 @@ local_step_kernel(int64_t N, int K, int Drt, int S, int PTS,
         T mx = s[0];
         for (int k = 1; k < K; ++k) mx = max(mx, s[k]);
         double se = 0.0;
-        for (int k = 0; k < K; ++k) se += exp((double)(s[k] - mx));
+        for (int k = 0; k < K; ++k) se += (double)t_exp(s[k] - mx);     // T-precision exp, double accumulation
         const T lse = mx + (T)log(se);
         for (int k = 0; k < K; ++k) s[k] -= lse;
     }
@@ -115,7 +115,7 @@ local_step_kernel(int64_t N, int K, int Drt, int S, int PTS,
     for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
         const T lr = sc[p];
         log_r[pt0 * K + p] = lr;
-        const double r = exp((double)lr);
+        const double r = (double)t_exp(lr);
         e_num += r * ((double)tnum[p] + (double)lr);
         e_den += r * (double)tden[p];
     }

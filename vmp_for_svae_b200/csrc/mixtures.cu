@@ -69,27 +69,42 @@ estep_consts_kernel(int K, int D, const T* __restrict__ alpha_k, const T* __rest
     }
 }
 
-template <typename T>
+// DT > 0: compile-time D (registers, fully unrolled quadratic form, symmetric: D(D+1)/2 FMAs); DT == 0: run-time D.
+// When all K components fit one shared-memory tile (the usual case) the row is normalised in the staging tile and
+// r / u are written exactly once, coalesced; otherwise un-normalised scores are written per tile and a second
+// coalesced pass over the CTA's contiguous [128 x K] block (an L2 hit) normalises them.
+template <typename T, int DT>
 __global__ void __launch_bounds__(ES_THREADS)
-estep_kernel(int64_t N, int K, int D, int KT, const T* __restrict__ x, const T* __restrict__ beta_k,
+estep_kernel(int64_t N, int K, int Drt, int KT, const T* __restrict__ x, const T* __restrict__ beta_k,
              const T* __restrict__ m_k, const T* __restrict__ P_k, const T* __restrict__ v_k,
              const T* __restrict__ kappa_k, const uint8_t* __restrict__ mask, const T* __restrict__ cst,
              T* __restrict__ r, T* __restrict__ u_out) {
-    extern __shared__ unsigned char smraw[];
-    T* Ps = reinterpret_cast<T*>(smraw);                 // [KT][D*D]
-    T* ms = Ps + (size_t)KT * D * D;                     // [KT][D]
-    T* stage = ms + (size_t)KT * D;                      // [ES_THREADS][KT+1]
-    T* stage2 = stage + (size_t)ES_THREADS * (KT + 1);   // [ES_THREADS][KT+1] (SMM: m_dist)
+    constexpr int DM = DT ? DT : VMP_MAX_D;
+    const int D = DT ? DT : Drt;
+    // DT > 0: one packed record per component, RS scalars, read back as 128-bit broadcasts:
+    //   tri[NP] (lower triangle, strictly-lower entries hold P_ic + P_ci) | m[D] | v, D/beta, cst, kappa
+    constexpr int NP = DM * (DM + 1) / 2;
+    constexpr int RS = DT ? ((NP + DT + 4 + 3) / 4) * 4 : 0;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    T* Ps = reinterpret_cast<T*>(smraw);                 // DT ? [KT][RS] : [KT][D*D]
+    T* ms = Ps + (DT ? (size_t)KT * RS : (size_t)KT * D * D);   // [KT][D]      (run-time D only)
+    T* ks = ms + (DT ? 0 : (size_t)KT * D);              // [KT][4]  v_k, D/beta_k, cst, kappa (run-time D only)
+    T* stage = ks + (DT ? 0 : (size_t)KT * 4);           // [ES_THREADS][KT+1]
+    T* stage2 = stage + (size_t)ES_THREADS * (KT + 1);   // [ES_THREADS][KT+1] (SMM: m_dist -> u)
     __shared__ T lse_s[ES_THREADS];
     const int tid = threadIdx.x;
     const int64_t n0 = (int64_t)blockIdx.x * ES_THREADS;
     const int64_t n = n0 + tid;
     const int np = (int)min((int64_t)ES_THREADS, N - n0);
     const bool smm = kappa_k != nullptr;
+    const bool single = KT >= K;
 
-    T xv[VMP_MAX_D];
-    if (n < N) {
-        for (int i = 0; i < D; ++i) xv[i] = x[n * D + i];
+    T xv[DM];
+    bool mk[DM];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        xv[i] = n < N ? x[n * D + i] : T(0);
+        mk[i] = (mask != nullptr && n < N) ? (mask[n * D + i] != 0) : false;
     }
     T run_max = -CUDART_INF_F;
     double run_sum = 0.0;
@@ -97,41 +112,85 @@ estep_kernel(int64_t N, int K, int D, int KT, const T* __restrict__ x, const T* 
     for (int kt0 = 0; kt0 < K; kt0 += KT) {
         const int kn = min(KT, K - kt0);
         __syncthreads();
-        for (int e = tid; e < kn * D * D; e += blockDim.x) Ps[e] = P_k[(size_t)kt0 * D * D + e];
-        for (int e = tid; e < kn * D; e += blockDim.x) ms[e] = m_k[(size_t)kt0 * D + e];
+        if (DT) {
+            for (int e = tid; e < kn * RS; e += blockDim.x) {
+                const int kk = e / RS, o = e - kk * RS, k = kt0 + kk;
+                const T* Pk = P_k + (size_t)k * D * D;
+                T v = T(0);
+                if (o < NP) {
+                    int i = 0;
+                    while ((i + 1) * (i + 2) / 2 <= o) ++i;
+                    const int c = o - i * (i + 1) / 2;
+                    v = c < i ? Pk[i * D + c] + Pk[c * D + i] : Pk[i * D + i];
+                } else if (o < NP + D) {
+                    v = m_k[(size_t)k * D + (o - NP)];
+                } else if (o == NP + D) {
+                    v = v_k[k];
+                } else if (o == NP + D + 1) {
+                    v = T(D) / beta_k[k];
+                } else if (o == NP + D + 2) {
+                    v = cst[k];
+                } else if (o == NP + D + 3) {
+                    v = smm ? kappa_k[k] : T(0);
+                }
+                Ps[e] = v;
+            }
+        } else {
+            for (int e = tid; e < kn * D * D; e += blockDim.x) Ps[e] = P_k[(size_t)kt0 * D * D + e];
+            for (int e = tid; e < kn * D; e += blockDim.x) ms[e] = m_k[(size_t)kt0 * D + e];
+            for (int e = tid; e < kn; e += blockDim.x) {
+                ks[4 * e + 0] = v_k[kt0 + e];
+                ks[4 * e + 1] = T(D) / beta_k[kt0 + e];
+                ks[4 * e + 2] = cst[kt0 + e];
+                ks[4 * e + 3] = smm ? kappa_k[kt0 + e] : T(0);
+            }
+        }
         __syncthreads();
         if (n < N) {
             for (int kk = 0; kk < kn; ++kk) {
-                const int k = kt0 + kk;
-                const T* P = Ps + (size_t)kk * D * D;
-                const T* m = ms + (size_t)kk * D;
-                T dv[VMP_MAX_D];
-                for (int i = 0; i < D; ++i) {
-                    T di = xv[i] - m[i];
-                    if (mask != nullptr && mask[n * D + i]) di = T(0);     // gmm.py:106-108
-                    dv[i] = di;
-                }
-                T q = T(0);
-                for (int i = 0; i < D; ++i) {
-                    T s = T(0);
-                    for (int c = 0; c < D; ++c) s = fma(P[i * D + c], dv[c], s);
-                    q = fma(dv[i], s, q);
-                }
-                const T md = v_k[k] * q + T(D) / beta_k[k];
-                T lr;
-                if (smm) {
-                    lr = cst[k] - T(0.5) * (T(D) + kappa_k[k]) * md;
-                    stage2[tid * (KT + 1) + kk] = md;
+                T dv[DM];
+                T q = T(0), kv, kdb, kc, kkap;
+                if (DT) {
+                    T rec[RS ? RS : 1];
+                    const T* rp = Ps + (size_t)kk * RS;
+#pragma unroll
+                    for (int o = 0; o < RS; ++o) rec[o] = rp[o];           // constant offsets: 128-bit broadcasts
+#pragma unroll
+                    for (int i = 0; i < D; ++i) dv[i] = mk[i] ? T(0) : xv[i] - rec[NP + i];      // gmm.py:106-108
+                    // triangular form: q = sum_i d_i (P_ii d_i + sum_{c<i} (P_ic + P_ci) d_c)
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        T s = T(0);
+#pragma unroll
+                        for (int c = 0; c < i; ++c) s = fma(rec[i * (i + 1) / 2 + c], dv[c], s);
+                        q = fma(dv[i], fma(rec[i * (i + 1) / 2 + i], dv[i], s), q);
+                    }
+                    kv = rec[NP + D]; kdb = rec[NP + D + 1]; kc = rec[NP + D + 2]; kkap = rec[NP + D + 3];
                 } else {
-                    lr = cst[k] - T(0.5) * md;
+                    const T* P = Ps + (size_t)kk * D * D;
+                    const T* m = ms + (size_t)kk * D;
+                    for (int i = 0; i < D; ++i) dv[i] = mk[i] ? T(0) : xv[i] - m[i];
+                    for (int i = 0; i < D; ++i) {
+                        T s = T(0);
+                        for (int c = 0; c < D; ++c) s = fma(P[i * D + c], dv[c], s);
+                        q = fma(dv[i], s, q);
+                    }
+                    kv = ks[4 * kk]; kdb = ks[4 * kk + 1]; kc = ks[4 * kk + 2]; kkap = ks[4 * kk + 3];
                 }
+                const T md = fma(kv, q, kdb);
+                const T lr = smm ? kc - T(0.5) * (T(D) + kkap) * md : kc - T(0.5) * md;
+                if (smm) stage2[tid * (KT + 1) + kk] = single ? (T(D) + kkap) / (md + kkap) : md;
                 stage[tid * (KT + 1) + kk] = lr;
                 if (lr > run_max) {
-                    run_sum = run_sum * exp((double)(run_max - lr)) + 1.0;
+                    run_sum = run_sum * (double)t_exp(run_max - lr) + 1.0;     // T-precision exp, double accumulation
                     run_max = lr;
                 } else {
-                    run_sum += exp((double)(lr - run_max));
+                    run_sum += (double)t_exp(lr - run_max);
                 }
+            }
+            if (single) {      // normalise this thread's row in the staging tile: r, u leave the SM exactly once
+                const T lse = run_max + (T)log(run_sum);
+                for (int kk = 0; kk < kn; ++kk) stage[tid * (KT + 1) + kk] = t_exp(stage[tid * (KT + 1) + kk] - lse);
             }
         }
         __syncthreads();
@@ -142,6 +201,7 @@ estep_kernel(int64_t N, int K, int D, int KT, const T* __restrict__ x, const T* 
             if (smm) u_out[(n0 + p) * K + kt0 + kk] = stage2[p * (KT + 1) + kk];
         }
     }
+    if (single) return;
     lse_s[tid] = (n < N) ? run_max + (T)log(run_sum) : T(0);
     __syncthreads();
     // normalisation pass over the contiguous [np x K] block
@@ -153,11 +213,27 @@ estep_kernel(int64_t N, int K, int D, int KT, const T* __restrict__ x, const T* 
     }
 }
 
+template <typename T, int DT>
+static int launch_estep(int64_t N, int K, int D, int KT, size_t smem, const T* x, const T* beta_k, const T* m_k,
+                        const T* P_k, const T* v_k, const T* kappa_k, const uint8_t* mask, const T* work, T* r, T* u_out,
+                        cudaStream_t st) {
+    auto kern = estep_kernel<T, DT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int64_t grid = (N + ES_THREADS - 1) / ES_THREADS;
+    if (grid > 0x7fffffffLL) return VMP_E_BADARG;
+    kern<<<(unsigned)grid, ES_THREADS, smem, st>>>(N, K, D, KT, x, beta_k, m_k, P_k, v_k, kappa_k, mask, work, r, u_out);
+    return launch_status();
+}
+
 template <typename T>
 int mixture_estep(int64_t N, int K, int D, const T* x, const T* alpha_k, const T* beta_k, const T* m_k, const T* P_k,
                   const T* v_k, const T* kappa_k, const uint8_t* mask, T* r, T* u_out, T* pi, T* work, void* stream) {
-    if (N < 0 || K <= 0 || !x || !alpha_k || !beta_k || !m_k || !P_k || !v_k || !r || !pi || !work) return VMP_E_BADARG;
-    if (kappa_k != nullptr && (u_out == nullptr || mask != nullptr)) return VMP_E_BADARG;
+    if (N < 0 || K <= 0 || !alpha_k || !beta_k || !m_k || !P_k || !v_k || !pi || !work) return VMP_E_BADARG;
+    if (N > 0 && (!x || !r)) return VMP_E_BADARG;
+    if (kappa_k != nullptr && ((N > 0 && u_out == nullptr) || mask != nullptr)) return VMP_E_BADARG;
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     cudaStream_t st = (cudaStream_t)stream;
     {
@@ -172,20 +248,19 @@ int mixture_estep(int64_t N, int K, int D, const T* x, const T* alpha_k, const T
     }
     if (N == 0) return VMP_OK;
     // components per shared-memory tile: as many as fit in ~96 KB together with the staging tiles
-    const size_t per_k = sizeof(T) * ((size_t)D * D + D + 2 * ES_THREADS);
+    const size_t rs = D <= 8 ? (size_t)((D * (D + 1) / 2 + D + 4 + 3) / 4) * 4 : (size_t)D * D + D + 4;
+    const size_t per_k = sizeof(T) * (rs + 2 * ES_THREADS);
     int KT = (int)((96 * 1024 - 2 * ES_THREADS * sizeof(T)) / per_k);
     if (KT < 1) KT = 1;
     if (KT > K) KT = K;
-    const size_t smem = sizeof(T) * ((size_t)KT * D * D + (size_t)KT * D + 2 * (size_t)ES_THREADS * (KT + 1));
-    auto kern = estep_kernel<T>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
+    const size_t smem = sizeof(T) * ((size_t)KT * rs + 2 * (size_t)ES_THREADS * (KT + 1)) + 16;
+#define VMP_ES(DD) \
+    case DD: return launch_estep<T, DD>(N, K, D, KT, smem, x, beta_k, m_k, P_k, v_k, kappa_k, mask, work, r, u_out, st)
+    switch (D) {
+        VMP_ES(1); VMP_ES(2); VMP_ES(3); VMP_ES(4); VMP_ES(5); VMP_ES(6); VMP_ES(7); VMP_ES(8);
+        default: return launch_estep<T, 0>(N, K, D, KT, smem, x, beta_k, m_k, P_k, v_k, kappa_k, mask, work, r, u_out, st);
     }
-    const int64_t grid = (N + ES_THREADS - 1) / ES_THREADS;
-    if (grid > 0x7fffffffLL) return VMP_E_BADARG;
-    kern<<<(unsigned)grid, ES_THREADS, smem, st>>>(N, K, D, KT, x, beta_k, m_k, P_k, v_k, kappa_k, mask, work, r, u_out);
-    return launch_status();
+#undef VMP_ES
 }
 
 }  // namespace vmp

@@ -202,6 +202,96 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
     }
 }
 
+// ---- small latent dimension (D <= 8: the C1-C3 shapes): lane <-> component --------------------------------------
+// A warp streams a run of points; lane l accumulates the (D+1)(D+2)/2 lower-triangular entries of w_nk xt xt^T for
+// component k = 32*blockIdx.y + l in registers (x is a warp-uniform broadcast load, r[n, k..k+31] one coalesced
+// 128-byte row).  fp32 partial sums cover at most SSM_RUN points, then go out as double atomics.
+constexpr int SSM_RUN = 256;       // points per warp run (fp32 partial sums)
+constexpr int SSM_WARPS = 8;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(SSM_WARPS * 32)
+suffstats_small_kernel(int64_t N, int K, const T* __restrict__ x, const T* __restrict__ r, int r_is_log,
+                       const T* __restrict__ u_nk, double* __restrict__ stats, int64_t pts_per_warp) {
+    constexpr int NA = (D + 1) * (D + 2) / 2;
+    __shared__ double red[NA + 1][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * SSM_WARPS + wib;
+    const int k = blockIdx.y * 32 + lane;
+    const int64_t n0 = min(N, warp * pts_per_warp), n1 = min(N, n0 + pts_per_warp);
+    T acc[NA];
+#pragma unroll
+    for (int e = 0; e < NA; ++e) acc[e] = T(0);
+    T racc = T(0);
+    const bool kin = k < K;
+    const T* rp = r + (kin ? k : 0);
+    const T* up = u_nk != nullptr ? u_nk + (kin ? k : 0) : nullptr;
+#pragma unroll 4
+    for (int64_t n = n0; n < n1; ++n) {
+        T xt[D + 1];
+#pragma unroll
+        for (int i = 0; i < D; ++i) xt[i] = x[n * D + i];
+        xt[D] = T(1);
+        T rv = rp[n * K];
+        if (r_is_log) rv = t_exp(rv);
+        if (!kin) rv = T(0);
+        const T w = up != nullptr ? rv * up[n * K] : rv;
+        racc += rv;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            const T wx = w * xt[i];
+#pragma unroll
+            for (int j = 0; j + 1 <= i; j += 2)
+                fma2_bcast(acc[i * (i + 1) / 2 + j], acc[i * (i + 1) / 2 + j + 1], wx, xt[j], xt[j + 1]);
+            if ((i & 1) == 0) acc[i * (i + 1) / 2 + i] = fma(wx, xt[i], acc[i * (i + 1) / 2 + i]);
+        }
+    }
+    // CTA reduction in double (lane <-> component is the same in every warp), then one atomic per entry per CTA
+    for (int wv = 0; wv < SSM_WARPS; ++wv) {
+        if (wib == wv) {
+#pragma unroll
+            for (int e = 0; e < NA; ++e) red[e][lane] = (wv == 0 ? 0.0 : red[e][lane]) + (double)acc[e];
+            red[NA][lane] = (wv == 0 ? 0.0 : red[NA][lane]) + (double)racc;
+        }
+        __syncthreads();
+    }
+    const int SL = stats_len(D);
+    for (int t = threadIdx.x; t < (NA + 1) * 32; t += blockDim.x) {
+        const int e = t >> 5, l = t & 31;
+        const int kk = blockIdx.y * 32 + l;
+        if (kk >= K) continue;
+        double* out = stats + (size_t)kk * SL;
+        const double v = red[e][l];
+        if (e == NA) { atomicAdd(out + 0, v); continue; }
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        const int j = e - i * (i + 1) / 2;
+        if (i < D) {
+            atomicAdd(out + 2 + D + i * D + j, v);
+            if (i != j) atomicAdd(out + 2 + D + j * D + i, v);
+        } else if (j < D) {
+            atomicAdd(out + 2 + j, v);
+        } else {
+            atomicAdd(out + 1, v);
+        }
+    }
+}
+
+template <typename T, int D>
+static int launch_suffstats_small(int64_t N, int K, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
+                                  cudaStream_t st) {
+    const int kblocks = (K + 31) / 32;
+    int64_t ppw = SSM_RUN;
+    const int64_t want_ctas = 148 * 2;
+    if ((N + ppw * SSM_WARPS - 1) / (ppw * SSM_WARPS) < want_ctas)
+        ppw = max((int64_t)8, (N + want_ctas * SSM_WARPS - 1) / (want_ctas * SSM_WARPS));
+    const int64_t grid = (N + ppw * SSM_WARPS - 1) / (ppw * SSM_WARPS);
+    if (grid > 0x7fffffffLL) return VMP_E_BADARG;
+    suffstats_small_kernel<T, D><<<dim3((unsigned)grid, kblocks), SSM_WARPS * 32, 0, st>>>(N, K, x, r, r_is_log, u_nk,
+                                                                                          stats, ppw);
+    return launch_status();
+}
+
 template <typename T>
 int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
               void* stream) {
@@ -209,6 +299,13 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     if (N == 0) return VMP_OK;
     if (!x || !r || !stats) return VMP_E_BADARG;
+#define VMP_SSM(DD) \
+    case DD: return launch_suffstats_small<T, DD>(N, K, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream)
+    switch (D) {
+        VMP_SSM(1); VMP_SSM(2); VMP_SSM(3); VMP_SSM(4); VMP_SSM(5); VMP_SSM(6); VMP_SSM(7); VMP_SSM(8);
+        default: break;
+    }
+#undef VMP_SSM
     const int D4 = ((D + 1 + 3) / 4) * 4;
     const int nb = D4 / 4;
     const int nt = nb * (nb + 1) / 2;

@@ -95,6 +95,24 @@ def m_step(x, r_nk, alpha_0, beta_0, m_0, C_0, v_0, name='m_step'):
     return core.mixture_mstep(stats, D, False, alpha_0, beta_0, m_0, C_0, v_0)
 
 
+_PRIOR_CACHE = {}
+
+
+def _prior_standard(K, D, seed, dtype, device):
+    """The sweep's Dirichlet+NIW prior in standard parameters (gmm.py: init_mm_params(...) -> niw.natural_to_standard,
+    dirichlet.natural_to_standard); constant for a given (K, D), so it is built once instead of every sweep."""
+    key = (K, D, int(seed), dtype, str(device))
+    if key not in _PRIOR_CACHE:
+        alpha, A, b, beta, v_hat = svae.init_mm_params(K, D, alpha_scale=0.05 / K, beta_scale=0.5, m_scale=0,
+                                                       C_scale=D + 0.5, v_init=D + 0.5, seed=seed, device=device,
+                                                       dtype=dtype)
+        beta_0, m_0, C_0, v_0 = niw.natural_to_standard(A, b, beta, v_hat)
+        alpha_0 = dirichlet.natural_to_standard(alpha)
+        _PRIOR_CACHE[key] = tuple(t.contiguous() for t in (alpha_0, beta_0, m_0, C_0, v_0))
+    return _PRIOR_CACHE[key]
+
+
+
 def inference(x, K, seed, name='inference', *, r_nk=None, dtype=None):
     """gmm.py:230-269 : one VB-EM sweep.  The reference keeps r_nk in a tf.Variable initialised from Dirichlet(1);
     here the state tensor is passed in (`r_nk=`, updated IN PLACE) or created on first use.
@@ -104,11 +122,7 @@ def inference(x, K, seed, name='inference', *, r_nk=None, dtype=None):
         g = torch.Generator(device='cpu').manual_seed(int(seed))
         e = -torch.log(torch.rand(N, K, generator=g, dtype=torch.float64))
         r_nk = (e / e.sum(1, keepdim=True)).to(device=x.device, dtype=x.dtype).contiguous()
-    alpha, A, b, beta, v_hat = svae.init_mm_params(K, D, alpha_scale=0.05 / K, beta_scale=0.5, m_scale=0,
-                                                   C_scale=D + 0.5, v_init=D + 0.5, seed=seed, device=x.device,
-                                                   dtype=x.dtype)
-    beta_0, m_0, C_0, v_0 = niw.natural_to_standard(A, b, beta, v_hat)
-    alpha_0 = dirichlet.natural_to_standard(alpha)
+    alpha_0, beta_0, m_0, C_0, v_0 = _prior_standard(K, D, seed, x.dtype, x.device)
     alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k = m_step(x, r_nk, alpha_0, beta_0.contiguous(), m_0.contiguous(),
                                                       C_0.contiguous(), v_0.contiguous())
     P_k, _ = core.spd_inverse(C_k, want_logdet=False)

@@ -90,6 +90,24 @@ def m_step(x, r_nk, u_nk, alpha_0, beta_0, m_0, C_0, v_0, name='m_step'):
     return core.mixture_mstep(stats, D, True, alpha_0, beta_0, m_0, C_0, v_0)
 
 
+_PRIOR_CACHE = {}
+
+
+def _prior_standard(K, D, seed, dtype, device):
+    """The sweep's Dirichlet+NIW prior in standard parameters (smm.py: init_mm_params(...) -> niw.natural_to_standard,
+    dirichlet.natural_to_standard); constant for a given (K, D), so it is built once instead of every sweep."""
+    key = (K, D, int(seed), dtype, str(device))
+    if key not in _PRIOR_CACHE:
+        alpha, A, b, beta, v_hat = svae.init_mm_params(K, D, alpha_scale=0.05 / K, beta_scale=0.5, m_scale=0,
+                                                       C_scale=D + 0.5, v_init=D + 0.5, seed=seed, device=device,
+                                                       dtype=dtype)
+        beta_0, m_0, C_0, v_0 = niw.natural_to_standard(A, b, beta, v_hat)
+        alpha_0 = dirichlet.natural_to_standard(alpha)
+        _PRIOR_CACHE[key] = tuple(t.contiguous() for t in (alpha_0, beta_0, m_0, C_0, v_0))
+    return _PRIOR_CACHE[key]
+
+
+
 def inference(x, K, kappa_init, seed, name='inference', *, r_nk=None, u_nk=None):
     """smm.py:199-245 : one VB-EM sweep; state (r_nk, u_nk) passed in / created, updated IN PLACE.
     Returns ((r_nk, u_nk), log_r_nk, theta, (x_k, S_k, pi))."""
@@ -100,11 +118,7 @@ def inference(x, K, kappa_init, seed, name='inference', *, r_nk=None, u_nk=None)
         r_nk = (e / e.sum(1, keepdim=True)).to(device=x.device, dtype=x.dtype).contiguous()
     if u_nk is None:
         u_nk = torch.ones(N, K, dtype=x.dtype, device=x.device)
-    alpha, A, b, beta, v_hat = svae.init_mm_params(K, D, alpha_scale=0.05 / K, beta_scale=0.5, m_scale=0,
-                                                   C_scale=D + 0.5, v_init=D + 0.5, seed=seed, device=x.device,
-                                                   dtype=x.dtype)
-    beta_0, m_0, C_0, v_0 = niw.natural_to_standard(A, b, beta, v_hat)
-    alpha_0 = dirichlet.natural_to_standard(alpha)
+    alpha_0, beta_0, m_0, C_0, v_0 = _prior_standard(K, D, seed, x.dtype, x.device)
     kappa_k = kappa_init * torch.ones(K, dtype=x.dtype, device=x.device)
     alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k = m_step(x, r_nk, u_nk, alpha_0, beta_0.contiguous(), m_0.contiguous(),
                                                       C_0.contiguous(), v_0.contiguous())
