@@ -138,6 +138,11 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -294,26 +299,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             });
 
             // ---------------- phase 2: right-looking Cholesky with the two forward substitutions riding along
-            float q = 0.f, hl = 0.f, pprod = 1.f;
+            float q = 0.f, hl2 = 0.f;                                     // hl2 = sum_j log2(pivot_j)
             static_for<0, D>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 constexpr int rj = j / BS, lj = j % BS;
                 const float piv = __shfl_sync(FULL, A[rj][j], lj, BS);
-                bad |= !(piv > 0.f);
                 float inv = rsqrt_approx(piv);                           // bare MUFU.RSQ (pivots are O(1): no denormals)
                 inv = inv * fmaf(-0.5f * piv * inv, inv, 1.5f);          // one Newton step: ~0.5 ulp
-                pprod *= piv;
-                if ((j & 3) == 3) { hl += logf(pprod); pprod = 1.f; }   // log of 4 pivots at a time (no overflow up to 1e9 each)
+                hl2 += lg2_approx(piv);                                  // bare MUFU.LG2 (rel. error 2^-22; NaN flags a bad pivot)
                 const float yj = __shfl_sync(FULL, g[rj] * inv, lj, BS);
                 const float y1j = __shfl_sync(FULL, g1[rj] * inv, lj, BS);
                 q = fmaf(yj, y1j, q);
-                const bool own = (gl == lj);
-                if (own) { ab[j] = yj; ib[j] = inv; }                    // kept in smem: frees 8 registers
+                if (gl == lj) { ab[j] = yj; ib[j] = inv; }               // kept in smem: frees 8 registers
                 float* cw = col + (j & 1) * D;
 #pragma unroll
                 for (int r = rj; r < ROWS; ++r) {
-                    float l = A[r][j] * inv;
-                    if (r == rj) l = own ? piv * inv : l;
+                    const float l = A[r][j] * inv;                       // owner's diagonal entry: piv * inv = L_jj
                     A[r][j] = l;
                     cw[r * BS + gl] = l;
                     ffma2_bcast(g[r], g1[r], -l, yj, y1j);
@@ -349,7 +350,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     }
                 });
             });
-            const float hld = 0.5f * hl;                          // sum_i log L_ii
+            const float hld = 0.5f * (float)VMP_LOG_2 * hl2;           // sum_i log L_ii
+            bad |= !(fabsf(hld) < CUDART_INF_F);                        // a non-positive pivot shows up as NaN / inf
             const float score = scl[0] - 0.5f * q + 0.5f * scl[1] - hld;
 
             // ---------------- phase 3: samples, ELBO terms
@@ -374,8 +376,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 for (int r = 0; r < ROWS; ++r) {
                     e2 = fmaf(w[r], w[r], e2);
                     w[r] -= ab[r * BS + gl];
-                    y[r] = 0.f;
                     idg[r] = ib[r * BS + gl];
+                    y[r] = 0.f;
                 }
                 // back substitution, block rows from the bottom
                 static_for_down<ROWS>([&](auto rbc) {
