@@ -239,6 +239,15 @@ def run_cuda(args):
         'kernel_ms': ms_kernel, 'kernel_share_of_step': ms_kernel / (ms_total / args.steps),
         'hbm_gbs_achieved': ach_gbs, 'hbm_frac': ach_gbs / peaks['hbm_gbs'], 'traffic': None,
     }
+    # measured DRAM traffic of this kernel (one ncu capture, profiles/): bytes per point x points of one launch
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic_local_step_fast64.json')) as f:
+            tr = json.load(f)
+        if (tr['K'], tr['D'], tr['S']) == (K, D, S):
+            roofline['traffic'] = tr['dram_bytes_per_point'] * n_per_gpu
+            roofline['traffic_source'] = tr['source']
+    except (OSError, ValueError, KeyError):
+        pass
     cpu = None
     if world == 1 or True:
         sample = args.cpu_sample or max(8, min(256, (1 << 22) // (K * D * D // 16 + 1)))
