@@ -179,6 +179,10 @@ int vmp_gaussian_logprob_nat_f32(int64_t N, int K, int S, int D, const float* x,
 int vmp_gaussian_logprob_nat_f64(int64_t N, int K, int S, int D, const double* x, const double* eta1,
                                  const double* eta2, const double* log_w, double* out, void* stream);
 
+/* FP32 pipe probe (measurement aid, not part of the reference surface): grid x 256 threads, each iters*128 FMAs as
+ * scalar FFMA (packed == 0) or packed FFMA2 / fma.rn.f32x2 (packed != 0); out[grid*256] floats.  Timed by the caller. */
+int vmp_fma_probe(int packed, int grid, int iters, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ _SIGS = {
     'vmp_theta_record_len': [c_int],
     'vmp_stats_len': [c_int],
     'vmp_svae_local_step_workspace_bytes': [c_int, c_int],
+    'vmp_fma_probe': [c_int, c_int, c_int, c_ptr, c_ptr],
 }
 EXPORTS = sorted(list(_SIGS) + [n + s for n in _SIGS_T for s in ('_f32', '_f64')])
 
