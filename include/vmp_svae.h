@@ -100,6 +100,29 @@ int vmp_svae_local_step_f64(int64_t N, int K, int D, int S, const double* eta1, 
  * without it (NULL / too small) the generic thread-per-pair kernels run instead.                       */
 size_t vmp_svae_local_step_workspace_bytes(int K, int D);
 
+/* ---- reverse pass of the fused local step ---------------------------------------------------------------
+ * Replaces what TF's autodiff builds for opt.compute_gradients(-elbo) (experiments.py:232) through svae.e_step
+ * (svae.py:39-100), the per-component sampling (svae.py:103-123) and the regulariser of compute_elbo / compute_elbo_smm
+ * (svae.py:199-322); theta is a constant there (tf.stop_gradient, svae.py:211-214).  Computes the gradients of
+ *      sum(gx * x_k_samples) + sum(glr * log_r) + greg * regulariser          (regulariser == elbo_acc[2] of the step)
+ * w.r.t. eta1[N,D], eta2_diag[N,D] and the raw phi_gmm (eta1_phi2[K,D], L_raw[K,D,D], pi_raw[K]).  The caller passes
+ * the same noise/seed and the log_r of the forward call; gx[N,K,S,D], glr[N,K] are the upstream gradients.
+ * D <= VMP_BWD_MAX_D, K <= 256.  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
+#define VMP_BWD_MAX_D 16
+size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D);
+int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
+                                const float* eta1_phi2, const float* L_raw, const float* pi_raw, const float* phi_rec,
+                                const float* theta_rec, int den_mode, const float* noise, uint64_t seed,
+                                const float* log_r, const float* gx, const float* glr, double greg, float* eta1_bar,
+                                float* eta2_diag_bar, float* eta1_phi2_bar, float* L_raw_bar, float* pi_raw_bar,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
+                                const double* eta1_phi2, const double* L_raw, const double* pi_raw,
+                                const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
+                                uint64_t seed, const double* log_r, const double* gx, const double* glr, double greg,
+                                double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
+                                double* pi_raw_bar, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The noise the in-kernel generator uses for a given seed, written in the reference layout
  * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N,K] (either may be NULL).      */
 int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, float* noise, float* u, void* stream);

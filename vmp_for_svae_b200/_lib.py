@@ -20,6 +20,9 @@ _SIGS_T = {
     'vmp_theta_prepare_student': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_svae_local_step': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_u64, c_ptr,
                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr],
+    'vmp_svae_local_step_bwd': [c_i64, c_int, c_int, c_int] + [c_ptr] * 7 + [c_int, c_ptr, c_u64, c_ptr, c_ptr, c_ptr,
+                                                                               c_dbl] + [c_ptr] * 5 +
+                               [c_ptr, ctypes.c_size_t, c_ptr],
     'vmp_fill_noise': [c_i64, c_int, c_int, c_int, c_u64, c_ptr, c_ptr, c_ptr],
     'vmp_suffstats': [c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr],
     'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_int] + [c_ptr] * 15 + [c_ptr],
@@ -35,6 +38,7 @@ _SIGS = {
     'vmp_theta_record_len': [c_int],
     'vmp_stats_len': [c_int],
     'vmp_svae_local_step_workspace_bytes': [c_int, c_int],
+    'vmp_svae_local_step_bwd_workspace_bytes': [c_int, c_int],
     'vmp_fma_probe': [c_int, c_int, c_int, c_ptr, c_ptr],
 }
 EXPORTS = sorted(list(_SIGS) + [n + s for n in _SIGS_T for s in ('_f32', '_f64')])

@@ -99,6 +99,33 @@ def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise
     return dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=x_k, elbo_acc=elbo_acc)
 
 
+def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, S, log_r, gx, glr, greg,
+                        den_mode=DEN_GAUSS, noise=None, seed=0):
+    """Reverse pass of the fused local step (vmp_svae_local_step_bwd): gradients of
+    sum(gx * x_k_samples) + sum(glr * log_r) + greg * regulariser w.r.t. (eta1, eta2_diag, eta1_phi2, L_raw, pi_raw).
+    `noise`/`seed` and `log_r` are those of the forward call; gx[N,K,S,D], glr[N,K]."""
+    N, D = eta1.shape
+    K = phi_rec.shape[0]
+    dt, dev = eta1.dtype, eta1.device
+    eta1 = _chk(eta1, (N, D), dt, 'eta1'); eta2_diag = _chk(eta2_diag, (N, D), dt, 'eta2_diag')
+    eta1_phi2 = _chk(eta1_phi2, (K, D), dt, 'eta1_phi2'); L_raw = _chk(L_raw, (K, D, D), dt, 'L_raw')
+    pi_raw = _chk(pi_raw, (K,), dt, 'pi_raw')
+    plen, tlen, _ = _lib.record_lens(D)
+    phi_rec = _chk(phi_rec, (K, plen), dt, 'phi_rec'); theta_rec = _chk(theta_rec, (K, tlen), dt, 'theta_rec')
+    log_r = _chk(log_r, (N, K), dt, 'log_r'); gx = _chk(gx, (N, K, S, D), dt, 'gx'); glr = _chk(glr, (N, K), dt, 'glr')
+    if noise is not None:
+        noise = _chk(noise, (N, K, D, S), dt, 'noise')
+    lib = _lib.load()
+    nbytes = int(lib.vmp_svae_local_step_bwd_workspace_bytes(K, D))
+    work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+    out = [torch.empty_like(t) for t in (eta1, eta2_diag, eta1_phi2, L_raw, pi_raw)]
+    _lib.call('vmp_svae_local_step_bwd', dt, N, K, D, S, ptr(eta1), ptr(eta2_diag), ptr(eta1_phi2), ptr(L_raw),
+              ptr(pi_raw), ptr(phi_rec), ptr(theta_rec), int(den_mode), ptr(noise), int(seed) & 0xFFFFFFFFFFFFFFFF,
+              ptr(log_r), ptr(gx), ptr(glr), float(greg), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
+              ptr(out[4]), ptr(work), nbytes, stream_ptr(dev))
+    return tuple(out)
+
+
 def fill_noise(N, K, D, S, seed, dtype, device, want_noise=True, want_u=True):
     noise = torch.empty(N, K, D, S, dtype=dtype, device=device) if want_noise else None
     u = torch.empty(N, K, dtype=dtype, device=device) if want_u else None

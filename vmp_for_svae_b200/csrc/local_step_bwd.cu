@@ -1,0 +1,443 @@
+// local_step_bwd.cu — reverse pass of the fused local step: gradients of
+//     sum(gx * x_k_samples) + sum(glr * log_r) + greg * regulariser
+// w.r.t. the encoder potentials (eta1, eta2_diag) and the raw recognition-GMM parameters (eta1_phi2, L_raw, pi_raw);
+// theta is behind the reference's tf.stop_gradient (svae.py:211-214).  This is what opt.compute_gradients(-elbo)
+// (experiments.py:232) back-propagates through svae.e_step / compute_elbo.  The per-pair formulas are those of
+// oracle/backward.py::backward_closed_form (checked against torch.autograd in tests/):
+//   Sig = P~^-1, mu~ = Sig eta~, u_s = L^-T eps_s, x_s = mu~ + u_s
+//   Gx_s = gx_s + greg/S * r W^T W (x_s - m);  glr' = glr + greg r (T + 1);  s_bar = glr' - r sum_k glr'
+//   P~_bar = -sym(v mu~^T) + sym(L^-T Phi(L^T L_bar) L^-1) + 1/2 (greg r - s_bar) Sig - 1/2 s_bar b b^T
+//            v = Sig sum_s Gx_s, L_bar = -tril(sum_s u_s (L^-1 Gx_s)^T), b = Sig P2 d
+//   d_bar = -s_bar P2 (d - b);  P2_bar = P~_bar - 1/2 s_bar (d d^T - d b^T - b d^T)  (+ K-sized terms in the epilogue)
+// One thread per (point, component) pair, latent dimension <= 16 (the reference's training shapes are D = 2 and 6);
+// per-point sums go through shared memory, per-component sums through double atomics, and a K-sized epilogue
+// kernel maps (P2_bar, mu2_bar, s_sum) back to (eta1_phi2, L_raw, pi_raw).
+#include "common.cuh"
+
+namespace vmp {
+
+constexpr int BWD_MAX_D = 16;
+
+template <typename T, int DT>
+__global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, int Drt, int S, int PTS, int den_mode, const T* __restrict__ eta1,
+                      const T* __restrict__ eta2d, const T* __restrict__ phi_rec, const T* __restrict__ theta_rec,
+                      const T* __restrict__ noise, uint64_t seed, const T* __restrict__ log_r,
+                      const T* __restrict__ gx, const T* __restrict__ glr, T greg,
+                      T* __restrict__ eta1_bar, T* __restrict__ eta2d_bar, double* __restrict__ kacc) {
+    constexpr int DM = DT ? DT : BWD_MAX_D;
+    const int D = DT ? DT : Drt;
+    extern __shared__ __align__(8) unsigned char smraw[];
+    double* pacc = reinterpret_cast<double*>(smraw);                 // [PTS][2*D]  eta1_bar | p1_bar per point
+    T* gsum = reinterpret_cast<T*>(pacc + (size_t)PTS * 2 * D);      // [PTS]       sum_k glr'
+    const int tid = threadIdx.x;
+    const int64_t pt0 = (int64_t)blockIdx.x * PTS;
+    const int npts = (int)min((int64_t)PTS, N - pt0);
+    const int pl = tid / K, k = tid - pl * K;
+    const bool act = pl < npts;
+    const int64_t n = pt0 + (act ? pl : 0);
+    for (int e = tid; e < PTS * 2 * D; e += blockDim.x) pacc[e] = 0.0;
+    for (int e = tid; e < PTS; e += blockDim.x) gsum[e] = T(0);
+    __syncthreads();
+
+    const int plen = phi_record_len(D), tlen = theta_record_len(D), kl = D * D + 2 * D + 1;
+    const T* prec = phi_rec + (size_t)k * plen;
+    const T* P2 = prec;
+    const T* trec = theta_rec + (size_t)k * tlen;
+    const T* W = trec;
+    const T* mth = trec + D * D;
+
+    T Lc[DM * DM], Li[DM * DM], Sg[DM * DM];      // L (lower), L^-1 (lower), Sig = P~^-1 (full)
+    T p1[DM], mu1[DM], dv[DM], bv[DM], mut[DM], gmu[DM], Lb[DM * DM];
+    T r = T(0), glrp = T(0), hldv = T(0);
+    if (act) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            p1[i] = T(-2) * eta2d[n * D + i];
+            mu1[i] = eta1[n * D + i] / p1[i];
+            dv[i] = mu1[i] - prec[D * D + i];
+        }
+        // L = chol(P2 + diag p1)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                T s = P2[i * D + j] + (i == j ? p1[i] : T(0));
+#pragma unroll
+                for (int c = 0; c < j; ++c) s = fma(-Lc[i * D + c], Lc[j * D + c], s);
+                Lc[i * D + j] = (i == j) ? t_sqrt(s) : s / Lc[j * D + j];
+            }
+        // L^-1 (lower), column by column
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            Li[j * D + j] = T(1) / Lc[j * D + j];
+#pragma unroll
+            for (int i = j + 1; i < D; ++i) {
+                T s = T(0);
+#pragma unroll
+                for (int c = j; c < i; ++c) s = fma(Lc[i * D + c], Li[c * D + j], s);
+                Li[i * D + j] = -s / Lc[i * D + i];
+            }
+        }
+        // Sig = L^-T L^-1
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                T s = T(0);
+#pragma unroll
+                for (int c = i; c < D; ++c) s = fma(Li[c * D + i], Li[c * D + j], s);
+                Sg[i * D + j] = s;
+                Sg[j * D + i] = s;
+            }
+        hldv = T(0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) hldv += t_log(Lc[i * D + i]);
+        // mu~ = Sig (eta1 + h2) ; b = Sig P2 d
+        T gq[DM];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int c = 0; c < D; ++c) s = fma(P2[i * D + c], dv[c], s);
+            gq[i] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            T s0 = T(0), s1 = T(0);
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                s0 = fma(Sg[i * D + c], eta1[n * D + c] + prec[D * D + D + c], s0);
+                s1 = fma(Sg[i * D + c], gq[c], s1);
+            }
+            mut[i] = s0;
+            bv[i] = s1;
+            gmu[i] = T(0);
+        }
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) Lb[e] = T(0);
+        r = t_exp(log_r[n * K + k]);
+        // samples: u_s, x_s, Gx_s, t_s ; accumulate gmu, L_bar, T
+        T Tsum = T(0);
+        for (int s = 0; s < S; ++s) {
+            T eps[DM], u[DM], Gx[DM], tv[DM], wx[DM];
+            const uint64_t pair = (uint64_t)n * K + k;
+            T e2 = T(0);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                eps[i] = noise != nullptr ? noise[(pair * D + i) * (uint64_t)S + s]
+                                          : (T)philox_normal1(seed, pair, (uint32_t)s, (uint32_t)i);
+                e2 = fma(eps[i], eps[i], e2);
+            }
+#pragma unroll
+            for (int ii = 0; ii < D; ++ii) {                       // u = L^-T eps
+                const int i = D - 1 - ii;
+                T sacc = eps[i];
+#pragma unroll
+                for (int c = i + 1; c < D; ++c) sacc = fma(-Lc[c * D + i], u[c], sacc);
+                u[i] = sacc / Lc[i * D + i];
+            }
+            T q2 = T(0);
+#pragma unroll
+            for (int i = 0; i < D; ++i) {                          // wx = W (x - m)
+                T sacc = T(0);
+#pragma unroll
+                for (int c = 0; c <= i; ++c) sacc = fma(W[i * D + c], mut[c] + u[c] - mth[c], sacc);
+                wx[i] = sacc;
+                q2 = fma(sacc, sacc, q2);
+            }
+            const T nu = trec[D * D + D + 1];
+            const T coef = den_mode == VMP_DEN_GAUSS ? T(1) : (nu + T(D)) / (nu + q2);      // d(-den)/d(q2/2)
+            const T* gxs = gx + ((pair * S) + s) * (uint64_t)D;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {                          // Gx = gx + greg/S r W^T wx
+                T sacc = T(0);
+#pragma unroll
+                for (int c = i; c < D; ++c) sacc = fma(W[c * D + i], wx[c], sacc);
+                Gx[i] = gxs[i] + greg / T(S) * r * coef * sacc;
+                gmu[i] += Gx[i];
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) {                          // t = L^-1 Gx
+                T sacc = T(0);
+#pragma unroll
+                for (int c = 0; c <= i; ++c) sacc = fma(Li[i * D + c], Gx[c], sacc);
+                tv[i] = sacc;
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) Lb[i * D + j] = fma(-u[i], tv[j], Lb[i * D + j]);
+            const T num = T(-0.5) * e2 + hldv - T(0.5 * VMP_LOG_2PI) * T(D) + log_r[n * K + k];
+            const T den = den_mode == VMP_DEN_GAUSS ? trec[D * D + D] - T(0.5) * q2
+                                                    : trec[D * D + D] - T(0.5) * (nu + T(D)) * t_log1p(q2 / nu);
+            Tsum += num - den;
+        }
+        glrp = glr[n * K + k] + greg * r * (Tsum / T(S) + T(1));
+        atomicAdd(&gsum[pl], glrp);
+    }
+    __syncthreads();
+    if (act) {
+    const T s_bar = glrp - r * gsum[pl];
+    const T hld_bar = greg * r - s_bar;
+
+    // v = Sig gmu ; Pt_bar (full symmetric) in Pb
+    T v[DM], Pb[DM * DM];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        T sacc = T(0);
+#pragma unroll
+        for (int c = 0; c < D; ++c) sacc = fma(Sg[i * D + c], gmu[c], sacc);
+        v[i] = sacc;
+    }
+    // Phi = tril(L^T L_bar), diagonal halved
+    T Ph[DM * DM];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            T sacc = T(0);
+#pragma unroll
+            for (int c = i; c < D; ++c) sacc = fma(Lc[c * D + i], Lb[c * D + j], sacc);
+            Ph[i * D + j] = (i == j) ? T(0.5) * sacc : sacc;
+        }
+    // Sm = L^-T Phi L^-1 ;  X = Phi Li (lower x lower -> lower), Sm = Li^T X
+    T X[DM * DM];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            T sacc = T(0);
+#pragma unroll
+            for (int c = j; c <= i; ++c) sacc = fma(Ph[i * D + c], Li[c * D + j], sacc);
+            X[i * D + j] = sacc;
+        }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            T sacc = T(0);
+#pragma unroll
+            for (int c = (i > j ? i : j); c < D; ++c) sacc = fma(Li[c * D + i], X[c * D + j], sacc);   // X[c][j]: j <= c
+            Pb[i * D + j] = sacc;                                   // Sm[i][j]
+        }
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const T sm = T(0.5) * (Pb[i * D + j] + Pb[j * D + i]);
+            const T val = sm - T(0.5) * (v[i] * mut[j] + mut[i] * v[j]) + T(0.5) * hld_bar * Sg[i * D + j]
+                          - T(0.5) * s_bar * bv[i] * bv[j];
+            Pb[i * D + j] = val;
+            Pb[j * D + i] = val;
+        }
+    // d_bar = -s_bar P2 (d - b)
+    T dbar[DM];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        T sacc = T(0);
+#pragma unroll
+        for (int c = 0; c < D; ++c) sacc = fma(P2[i * D + c], dv[c] - bv[c], sacc);
+        dbar[i] = -s_bar * sacc;
+    }
+    // per-point sums: eta1_bar += v + d_bar / p1 ; p1_bar += diag(Pt_bar) - d_bar * eta1 / p1^2
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        atomicAdd(&pacc[(size_t)pl * 2 * D + i], (double)(v[i] + dbar[i] / p1[i]));
+        atomicAdd(&pacc[(size_t)pl * 2 * D + D + i], (double)(Pb[i * D + i] - dbar[i] * mu1[i] / p1[i]));
+    }
+    // per-component sums (double atomics): P2_bar | h2_bar (v) | mu2_bar (-d_bar) | s_sum
+    double* ka = kacc + (size_t)k * kl;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const T val = Pb[i * D + j] - T(0.5) * s_bar * (dv[i] * dv[j] - dv[i] * bv[j] - bv[i] * dv[j]);
+            atomicAdd(ka + i * D + j, (double)val);
+        }
+        atomicAdd(ka + D * D + i, (double)v[i]);
+        atomicAdd(ka + D * D + D + i, (double)(-dbar[i]));
+    }
+    atomicAdd(ka + D * D + 2 * D, (double)s_bar);
+    }
+    __syncthreads();
+    for (int e = tid; e < npts * D; e += blockDim.x) {             // per-point results out of the shared accumulators
+        const int q = e / D, i = e - q * D;
+        eta1_bar[(pt0 + q) * D + i] = (T)pacc[(size_t)q * 2 * D + i];
+        eta2d_bar[(pt0 + q) * D + i] = (T)(-2.0 * pacc[(size_t)q * 2 * D + D + i]);
+    }
+}
+
+// K-sized epilogue: (P2_bar, h2_bar, mu2_bar, s_sum) -> (eta1_phi2_bar, L_raw_bar, pi_raw_bar)
+template <typename T>
+__global__ void __launch_bounds__(128)
+local_step_bwd_epilogue_kernel(int K, int D, const T* __restrict__ eta1_phi2, const T* __restrict__ L_raw,
+                               const T* __restrict__ pi_raw, const double* __restrict__ kacc,
+                               T* __restrict__ h2_bar, T* __restrict__ L_raw_bar, T* __restrict__ pi_raw_bar) {
+    extern __shared__ double sm[];
+    const int ld = D + 1;
+    double* L2 = sm;                 // D x ld
+    double* Wi = L2 + D * ld;        // L2^-1
+    double* Pi = Wi + D * ld;        // P2^-1
+    double* Pb = Pi + D * ld;        // P2_bar (full)
+    double* vec = Pb + D * ld;       // mu2 | w2 | mu2_bar
+    double* red = vec + 3 * D;
+    const int k = blockIdx.x, kl = D * D + 2 * D + 1;
+    const double* ka = kacc + (size_t)k * kl;
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e % D;
+        double v = 0.0;
+        if (j < i) v = (double)L_raw[(size_t)k * D * D + e];
+        else if (j == i) v = t_softplus<double>((double)L_raw[(size_t)k * D * D + e]);
+        L2[i * ld + j] = v;
+        Pb[i * ld + j] = ka[e];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < D; j += blockDim.x) {             // Wi = L2^-1, column j
+        for (int i = 0; i < j; ++i) Wi[i * ld + j] = 0.0;
+        Wi[j * ld + j] = 1.0 / L2[j * ld + j];
+        for (int i = j + 1; i < D; ++i) {
+            double s = 0.0;
+            for (int c = j; c < i; ++c) s += L2[i * ld + c] * Wi[c * ld + j];
+            Wi[i * ld + j] = -s / L2[i * ld + i];
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {         // P2^-1 = Wi^T Wi
+        const int i = e / D, j = e % D;
+        const int m = i > j ? i : j;
+        double s = 0.0;
+        for (int c = m; c < D; ++c) s += Wi[c * ld + i] * Wi[c * ld + j];
+        Pi[i * ld + j] = s;
+    }
+    __syncthreads();
+    const double s_sum = ka[D * D + 2 * D];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        double mu2 = 0.0, w2 = 0.0;
+        for (int c = 0; c < D; ++c) {
+            mu2 += Pi[i * ld + c] * (double)eta1_phi2[(size_t)k * D + c];
+            w2 += Pi[i * ld + c] * ka[D * D + D + c];
+        }
+        vec[i] = mu2;
+        vec[D + i] = w2;
+        h2_bar[(size_t)k * D + i] = (T)(ka[D * D + i] + w2);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e % D;
+        Pb[i * ld + j] += 0.5 * s_sum * Pi[i * ld + j] - 0.5 * (vec[D + i] * vec[j] + vec[i] * vec[D + j]);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {         // L2_bar = tril((Pb + Pb^T) L2), softplus' on the diagonal
+        const int i = e / D, j = e % D;
+        double g = 0.0;
+        if (j <= i) {
+            for (int c = j; c < D; ++c) g += (Pb[i * ld + c] + Pb[c * ld + i]) * L2[c * ld + j];
+            if (j == i) g *= 1.0 / (1.0 + exp(-(double)L_raw[(size_t)k * D * D + e]));
+        }
+        L_raw_bar[(size_t)k * D * D + e] = (T)g;
+    }
+    // pi_raw_bar = s_sum - softmax(pi_raw) * sum_k s_sum
+    double mx = -CUDART_INF, tot = 0.0;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) mx = fmax(mx, (double)pi_raw[j]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmax(mx, red[w]);
+    __syncthreads();
+    double se = 0.0;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        se += exp((double)pi_raw[j] - mx);
+        tot += kacc[(size_t)j * kl + D * D + 2 * D];
+    }
+    se = block_sum(se, red);
+    __shared__ double bse;
+    if (threadIdx.x == 0) bse = se;
+    __syncthreads();
+    tot = block_sum(tot, red);
+    if (threadIdx.x == 0) pi_raw_bar[k] = (T)(s_sum - exp((double)pi_raw[k] - mx) / bse * tot);
+}
+
+template <typename T, int DT>
+static cudaError_t launch_bwd_main(int64_t N, int K, int D, int S, int den_mode, const T* eta1, const T* eta2d,
+                                   const T* phi_rec, const T* theta_rec, const T* noise, uint64_t seed, const T* log_r,
+                                   const T* gx, const T* glr, T greg, T* eta1_bar, T* eta2d_bar, double* kacc,
+                                   cudaStream_t st) {
+    const int PTS = K >= 128 ? 1 : 128 / K;
+    const int threads = ((PTS * K + 31) / 32) * 32;
+    const size_t smem = (size_t)PTS * 2 * D * sizeof(double) + (size_t)PTS * sizeof(T);
+    const int64_t grid = (N + PTS - 1) / PTS;
+    local_step_bwd_kernel<T, DT><<<(unsigned)grid, threads, smem, st>>>(N, K, D, S, PTS, den_mode, eta1, eta2d, phi_rec,
+                                                                        theta_rec, noise, seed, log_r, gx, glr, greg,
+                                                                        eta1_bar, eta2d_bar, kacc);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* eta1_phi2,
+                               const T* L_raw, const T* pi_raw, const T* phi_rec, const T* theta_rec, int den_mode,
+                               const T* noise, uint64_t seed, const T* log_r, const T* gx, const T* glr, double greg,
+                               T* eta1_bar, T* eta2d_bar, T* h2_bar, T* L_raw_bar, T* pi_raw_bar, void* work,
+                               size_t work_bytes, cudaStream_t st) {
+    if (N < 0 || K < 1 || K > 256 || S < 1) return VMP_E_BADARG;
+    if (D < 1 || D > BWD_MAX_D) return VMP_E_BADDIM;
+    if (den_mode != VMP_DEN_GAUSS && den_mode != VMP_DEN_STUDENT) return VMP_E_BADMODE;
+    const size_t kl = (size_t)D * D + 2 * D + 1;
+    if (!work || work_bytes < (size_t)K * kl * sizeof(double)) return VMP_E_BADARG;
+    if (!eta1_phi2 || !L_raw || !pi_raw || !h2_bar || !L_raw_bar || !pi_raw_bar) return VMP_E_BADARG;
+    double* kacc = static_cast<double*>(work);
+    { cudaError_t me = cudaMemsetAsync(kacc, 0, (size_t)K * kl * sizeof(double), st); if (me != cudaSuccess) return (int)me; }
+    if (N > 0) {
+        if (!eta1 || !eta2d || !phi_rec || !theta_rec || !log_r || !gx || !glr || !eta1_bar || !eta2d_bar)
+            return VMP_E_BADARG;
+        cudaError_t e;
+#define VMP_BWD_CASE(DD)                                                                                              \
+    case DD:                                                                                                          \
+        e = launch_bwd_main<T, DD>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise, seed, log_r, gx, glr, \
+                                   (T)greg, eta1_bar, eta2d_bar, kacc, st);                                           \
+        break;
+        switch (D) {
+            VMP_BWD_CASE(1) VMP_BWD_CASE(2) VMP_BWD_CASE(3) VMP_BWD_CASE(4) VMP_BWD_CASE(5) VMP_BWD_CASE(6)
+            VMP_BWD_CASE(7) VMP_BWD_CASE(8)
+            default:
+                e = launch_bwd_main<T, 0>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise, seed, log_r, gx,
+                                          glr, (T)greg, eta1_bar, eta2d_bar, kacc, st);
+        }
+#undef VMP_BWD_CASE
+        if (e != cudaSuccess) return (int)e;
+    }
+    const size_t esm = (size_t)(4 * D * (D + 1) + 3 * D + 32) * sizeof(double);
+    local_step_bwd_epilogue_kernel<T><<<K, 128, esm, st>>>(K, D, eta1_phi2, L_raw, pi_raw, kacc, h2_bar, L_raw_bar,
+                                                           pi_raw_bar);
+    return launch_status();
+}
+
+}  // namespace vmp
+
+extern "C" {
+size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D) {
+    return (size_t)K * ((size_t)D * D + 2 * D + 1) * sizeof(double);
+}
+int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
+                                const float* eta1_phi2, const float* L_raw, const float* pi_raw, const float* phi_rec,
+                                const float* theta_rec, int den_mode, const float* noise, uint64_t seed,
+                                const float* log_r, const float* gx, const float* glr, double greg, float* eta1_bar,
+                                float* eta2_diag_bar, float* eta1_phi2_bar, float* L_raw_bar, float* pi_raw_bar,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    return vmp::svae_local_step_bwd<float>(N, K, D, S, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec,
+                                           den_mode, noise, seed, log_r, gx, glr, greg, eta1_bar, eta2_diag_bar,
+                                           eta1_phi2_bar, L_raw_bar, pi_raw_bar, workspace, workspace_bytes,
+                                           static_cast<cudaStream_t>(stream));
+}
+int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
+                                const double* eta1_phi2, const double* L_raw, const double* pi_raw,
+                                const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
+                                uint64_t seed, const double* log_r, const double* gx, const double* glr, double greg,
+                                double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
+                                double* pi_raw_bar, void* workspace, size_t workspace_bytes, void* stream) {
+    return vmp::svae_local_step_bwd<double>(N, K, D, S, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec,
+                                            den_mode, noise, seed, log_r, gx, glr, greg, eta1_bar, eta2_diag_bar,
+                                            eta1_phi2_bar, L_raw_bar, pi_raw_bar, workspace, workspace_bytes,
+                                            static_cast<cudaStream_t>(stream));
+}
+}
