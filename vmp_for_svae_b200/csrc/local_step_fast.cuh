@@ -7,8 +7,9 @@
 //   * right-looking Cholesky: at step j the pivot is broadcast with one shuffle, every lane scales its own entries
 //     of column j, publishes them to a 2 x D shared-memory column buffer, and updates its rows with the column read
 //     back as 128-bit broadcasts.  The update is issued as packed FFMA2 (PTX fma.rn.f32x2, sm_100): two FMAs per
-//     instruction with the row's multiplier as broadcast scalar operand — measured 1.65x over scalar FFMA, which on
-//     this part cannot reach the FP32 peak (profiles/);
+//     instruction with the row's multiplier as broadcast scalar operand — measured 1.65x over scalar FFMA in THIS
+//     kernel because it halves the issue slots and the instruction footprint (the scalar build was instruction-fetch
+//     bound; in a pure register loop both forms reach the pipe's peak, tools/fp32_peak.py);
 //   * the two forward substitutions a = L^-1 P2 d, a1 = L^-1 P1 d ride along as a packed right-hand-side pair;
 //   * back substitution L^T y = eps - a goes block by block (BS x BS) with the blocks transposed through a padded
 //     shared-memory tile, the solved block broadcast through shared memory;
