@@ -107,7 +107,9 @@ size_t vmp_svae_local_step_workspace_bytes(int K, int D);
  *      sum(gx * x_k_samples) + sum(glr * log_r) + greg * regulariser          (regulariser == elbo_acc[2] of the step)
  * w.r.t. eta1[N,D], eta2_diag[N,D] and the raw phi_gmm (eta1_phi2[K,D], L_raw[K,D,D], pi_raw[K]).  The caller passes
  * the same noise/seed and the log_r of the forward call; gx[N,K,S,D], glr[N,K] are the upstream gradients.
- * D <= VMP_BWD_MAX_D, K <= 256.  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
+ * theta_rec_bar[K, vmp_theta_record_len(D)] (may be NULL) receives the gradient w.r.t. the theta record (W lower | m |
+ * cden, zeros): compute_elbo_smm trains mu_k, L_k of the Student-t components by gradient (svae.py:265-322 has no
+ * stop_gradient on them; experiments.py:154-174).  D <= VMP_BWD_MAX_D, K <= 256.  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
 #define VMP_BWD_MAX_D 16
 size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D);
 int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
@@ -115,13 +117,14 @@ int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta
                                 const float* theta_rec, int den_mode, const float* noise, uint64_t seed,
                                 const float* log_r, const float* gx, const float* glr, double greg, float* eta1_bar,
                                 float* eta2_diag_bar, float* eta1_phi2_bar, float* L_raw_bar, float* pi_raw_bar,
-                                void* workspace, size_t workspace_bytes, void* stream);
+                                float* theta_rec_bar, void* workspace, size_t workspace_bytes, void* stream);
 int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
                                 const double* eta1_phi2, const double* L_raw, const double* pi_raw,
                                 const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
                                 uint64_t seed, const double* log_r, const double* gx, const double* glr, double greg,
                                 double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
-                                double* pi_raw_bar, void* workspace, size_t workspace_bytes, void* stream);
+                                double* pi_raw_bar, double* theta_rec_bar, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* The noise the in-kernel generator uses for a given seed, written in the reference layout
  * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N,K] (either may be NULL).      */
@@ -192,6 +195,16 @@ int vmp_decoder_loglike_f32(int64_t N, int K, int S, int Dobs, int mode, const f
                             const float* out2, const float* w, double* acc, void* stream);
 int vmp_decoder_loglike_f64(int64_t N, int K, int S, int Dobs, int mode, const double* y, const double* means,
                             const double* out2, const double* w, double* acc, void* stream);
+
+/* Reverse of the reduction above (what TF's autodiff builds for the neg_rec term of the ELBO, svae.py:220-223):
+ * g_means = scale * d acc/d means, g_out2 = scale * d acc/d out2 [N,K,S,Dobs]; g_w = scale * d acc/d w [N,K] (may be
+ * NULL).  mode 1 ignores means / g_means.                                                                */
+int vmp_decoder_loglike_bwd_f32(int64_t N, int K, int S, int Dobs, int mode, const float* y, const float* means,
+                                const float* out2, const float* w, double scale, float* g_means, float* g_out2,
+                                float* g_w, void* stream);
+int vmp_decoder_loglike_bwd_f64(int64_t N, int K, int S, int Dobs, int mode, const double* y, const double* means,
+                                const double* out2, const double* w, double scale, double* g_means, double* g_out2,
+                                double* g_w, void* stream);
 
 /* General dense-natural-parameter Gaussian log-density (API surface of distributions/gaussian.py).
  * S == 0: gaussian.log_probability_nat (gaussian.py:30-71): x[N,D], eta1[N,K,D], eta2[N,K,D,D], log_w[K] or NULL

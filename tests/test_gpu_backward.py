@@ -125,3 +125,65 @@ def test_backward_argument_errors():
     with pytest.raises(Exception):
         core.local_step_backward(z(N, 2).cpu(), z(N, 2), z(K, 2), z(K, 2, 2), z(K), z(K, 12), z(K, 10), S, z(N, K),
                                  z(N, K, S, 2), z(N, K), 1.0)
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('shape', [(100, 10, 2, 10), (274, 10, 6, 10), (33, 5, 11, 3)], ids=lambda s: 'N%dK%dD%dS%d' % s)
+def test_backward_theta_record_gradient(shape, dt):
+    """SMM variant: mu_k, L_k of the Student-t components are trained by gradient (experiments.py:154-174), so the
+    reverse pass also returns d/d(theta record); checked against autograd through the oracle w.r.t. (W, m, cden)."""
+    from oracle import backward as ob
+    from vmp_for_svae_b200 import core
+    from vmp_for_svae_b200.autograd import local_step_autograd, student_theta_record
+    N, K, D, S = shape
+    theta, phi_gmm, phi_enc, noise, gx, glr, greg = _inputs(N, K, D, S, seed=5 + N, student=True)
+    W, m, cden, nu = ob.theta_consts_student(theta)
+    lv = [t.clone().requires_grad_(True) for t in (W, m, cden)]
+    x, log_r, reg = ob.forward(phi_enc[0], phi_enc[1], phi_gmm[0], phi_gmm[1], phi_gmm[2], lv[0], lv[1], lv[2], noise, nu=nu)
+    ref = torch.autograd.grad((gx * x).sum() + (glr * log_r).sum() + greg * reg, lv)
+    dev = lambda t: t.to(device=DEV, dtype=dt).contiguous()
+    th = [dev(t) for t in theta]
+    rec0 = core.theta_prepare_student(th)
+    leaves = [dev(t).requires_grad_(True) for t in theta[1:3]]
+    rec = student_theta_record(th[0], leaves[0], leaves[1], th[3])
+    assert torch.allclose(rec, rec0, rtol=1e-10 if dt == torch.float64 else 1e-5, atol=1e-12 if dt == torch.float64 else 1e-6)
+    rec_leaf = rec.detach().clone().requires_grad_(True)
+    args = [dev(t) for t in (phi_enc[0], phi_enc[1], phi_gmm[0], phi_gmm[1], phi_gmm[2])]
+    xg, lrg, regg, _ = local_step_autograd(*args, rec_leaf, S, den_mode=core.DEN_STUDENT, noise=dev(noise))
+    (g_rec,) = torch.autograd.grad((dev(gx) * xg).sum() + (dev(glr) * lrg).sum() + greg * regg, [rec_leaf])
+    g_rec = g_rec.cpu().double()
+    tol = 1e-8 if dt == torch.float64 else 2e-3
+    gW, gm, gc = g_rec[:, :D * D].reshape(K, D, D), g_rec[:, D * D:D * D + D], g_rec[:, D * D + D]
+    for name, a, b in (('W', gW, torch.tril(ref[0])), ('m', gm, ref[1]), ('cden', gc, ref[2])):
+        err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+        assert err < tol, (name, err)
+    assert float(g_rec[:, D * D + D + 1:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('mode', ['standard', 'bernoulli'])
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+def test_decoder_loglike_backward(mode, dt):
+    """neg_rec term (vae.py:175-250) forward + reverse against autograd through the oracle restatement."""
+    from oracle import svae_port as sp
+    from vmp_for_svae_b200.autograd import decoder_loglike_autograd
+    rs = np.random.RandomState(2)
+    N, K, S, Do = 37, 5, 3, 45
+    y = T(np.sign(rs.randn(N, Do))) if mode == 'bernoulli' else T(rs.randn(N, Do))
+    means, out2 = T(rs.randn(N, K, S, Do)), T(rs.randn(N, K, S, Do))
+    if mode == 'standard':
+        out2 = torch.nn.functional.softplus(out2) + 0.05
+    w = T(rs.dirichlet(np.ones(K), N))
+    lv = [t.clone().requires_grad_(True) for t in (means, out2, w)]
+    val = sp.expected_diagonal_gaussian_loglike(y, lv[0], lv[1], weights=lv[2]) if mode == 'standard' \
+        else sp.expected_bernoulli_loglike(y, lv[1], r_nk=lv[2])
+    ref = torch.autograd.grad(val, lv, allow_unused=True)
+    dev = lambda t: t.to(device=DEV, dtype=dt).contiguous()
+    lg = [dev(t).requires_grad_(True) for t in (means, out2, w)]
+    got_val = decoder_loglike_autograd(dev(y), (lg[0], lg[1]), lg[2], mode)
+    got = torch.autograd.grad(got_val * 1.5, lg, allow_unused=True)
+    tol = 1e-10 if dt == torch.float64 else 2e-5
+    assert abs(float(got_val) - float(val)) <= tol * abs(float(val))
+    for a, b in zip(got, ref):
+        if b is None:
+            continue
+        assert float((a.cpu().double() / 1.5 - b).abs().max() / b.abs().max()) < tol

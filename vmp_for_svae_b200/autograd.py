@@ -39,14 +39,69 @@ class _LocalStepFn(torch.autograd.Function):
         gx = torch.zeros(N, K, ctx.S, D, dtype=eta1.dtype, device=eta1.device) if gx is None else gx.contiguous()
         glr = torch.zeros(N, K, dtype=eta1.dtype, device=eta1.device) if glr is None else glr.contiguous()
         greg = 0.0 if greg is None else float(greg)     # one scalar sync; the loss weight is 1 or -1 in practice
+        want_th = ctx.needs_input_grad[5]
         g = core.local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, ctx.S, log_r, gx,
-                                     glr, greg, den_mode=ctx.den_mode, noise=ctx.noise, seed=ctx.seed)
-        return g[0], g[1], g[2], g[3], g[4], None, None, None, None, None
+                                     glr, greg, den_mode=ctx.den_mode, noise=ctx.noise, seed=ctx.seed,
+                                     want_theta_rec_bar=want_th)
+        return g[0], g[1], g[2], g[3], g[4], (g[5] if want_th else None), None, None, None, None
 
 
 def local_step_autograd(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, S, den_mode=core.DEN_GAUSS, seed=0,
                         noise=None):
     """-> (x_k_samples[N,K,S,D], log_r[N,K], regulariser (0-d), elbo_acc[4] double, non-differentiable).
-    theta_rec comes from core.theta_prepare_* (a constant of the graph, as in the reference)."""
+    theta_rec comes from core.theta_prepare_* (a constant of the graph for the GMM prior, as in the reference) or from
+    `student_theta_record` below (differentiable: the SMM variant trains mu_k, L_k by gradient)."""
     return _LocalStepFn.apply(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, int(S), int(den_mode), int(seed),
                               noise)
+
+
+def student_theta_record(alpha_nat, mu_k, L_k_raw, dof):
+    """Differentiable theta record of the Student-t denominator (svae.py:265-306; svae.unpack_smm 361-373):
+    Sigma_k = L L^T with L = tril(L_raw), softplus on the diagonal, so chol(Sigma_k) = L and W_k = L^-1.  K-sized torch
+    ops (plumbing); E log pi and the degrees of freedom carry no gradient (svae.py:275-277).  Same layout and values as
+    core.theta_prepare_student."""
+    K, D = mu_k.shape
+    L = torch.tril(L_k_raw, -1) + torch.diag_embed(torch.nn.functional.softplus(torch.diagonal(L_k_raw, dim1=-2, dim2=-1)))
+    W = torch.linalg.solve_triangular(L, torch.eye(D, dtype=mu_k.dtype, device=mu_k.device).expand(K, D, D), upper=False)
+    alpha = (alpha_nat + 1.0).detach()
+    e_log_pi = torch.digamma(alpha) - torch.digamma(alpha.sum())
+    nu = dof.detach()
+    logdet_half = torch.log(torch.diagonal(L, dim1=-2, dim2=-1)).sum(-1)
+    import math
+    cden = e_log_pi + torch.lgamma((nu + D) / 2.0) - torch.lgamma(nu / 2.0) - 0.5 * D * torch.log(nu * math.pi) - logdet_half
+    return torch.cat([W.reshape(K, D * D), mu_k, cden.unsqueeze(1), nu.unsqueeze(1), e_log_pi.unsqueeze(1),
+                      (-2.0 * logdet_half).unsqueeze(1)], dim=1)
+
+
+class _DecoderLoglikeFn(torch.autograd.Function):
+    """neg_rec term of the ELBO (svae.py:220-223): vae.expected_diagonal_gaussian_loglike (mode 0, vae.py:226-248) or
+    vae.expected_bernoulli_loglike (mode 1, vae.py:175-198) with responsibilities as weights; one streaming kernel each
+    way over the decoder outputs [N,K,S,Dobs]."""
+
+    @staticmethod
+    def forward(ctx, y, means, out2, w, mode):
+        import math
+        N, K, S, Dobs = out2.shape
+        y, out2, w = y.contiguous(), out2.contiguous(), w.contiguous()
+        means = means.contiguous() if mode == 0 else None
+        acc = core.decoder_loglike(y, means, out2, w, mode)
+        ctx.save_for_backward(y, means, out2, w)
+        ctx.mode = mode
+        ctx.scale = -0.5 / S if mode == 0 else 1.0 / S
+        val = acc[0] * ctx.scale - (N * Dobs / 2.0 * math.log(2.0 * math.pi) if mode == 0 else 0.0)
+        return val.to(out2.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        y, means, out2, w = ctx.saved_tensors
+        g_means, g_out2, g_w = core.decoder_loglike_backward(y, means, out2, w, ctx.mode, ctx.scale)
+        return None, (g_means * g if g_means is not None else None), g_out2 * g, g_w * g, None
+
+
+def decoder_loglike_autograd(y, reconstructions, r_nk, decoder_type):
+    """Differentiable `neg_rec` of svae.compute_elbo: reconstructions = (means, out_2) [N,K,S,Dobs], r_nk [N,K]."""
+    means, out2 = reconstructions
+    mode = {'standard': 0, 'bernoulli': 1}[decoder_type]
+    if mode == 1 and means is None:
+        means = out2
+    return _DecoderLoglikeFn.apply(y, means, out2, r_nk, mode)

@@ -100,10 +100,11 @@ def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise
 
 
 def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, S, log_r, gx, glr, greg,
-                        den_mode=DEN_GAUSS, noise=None, seed=0):
+                        den_mode=DEN_GAUSS, noise=None, seed=0, want_theta_rec_bar=False):
     """Reverse pass of the fused local step (vmp_svae_local_step_bwd): gradients of
     sum(gx * x_k_samples) + sum(glr * log_r) + greg * regulariser w.r.t. (eta1, eta2_diag, eta1_phi2, L_raw, pi_raw).
-    `noise`/`seed` and `log_r` are those of the forward call; gx[N,K,S,D], glr[N,K]."""
+    `noise`/`seed` and `log_r` are those of the forward call; gx[N,K,S,D], glr[N,K].  With want_theta_rec_bar the
+    gradient w.r.t. the theta record (W | m | cden) is appended (the SMM variant trains mu_k, L_k by gradient)."""
     N, D = eta1.shape
     K = phi_rec.shape[0]
     dt, dev = eta1.dtype, eta1.device
@@ -119,11 +120,12 @@ def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, thet
     nbytes = int(lib.vmp_svae_local_step_bwd_workspace_bytes(K, D))
     work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
     out = [torch.empty_like(t) for t in (eta1, eta2_diag, eta1_phi2, L_raw, pi_raw)]
+    th_bar = torch.empty_like(theta_rec) if want_theta_rec_bar else None
     _lib.call('vmp_svae_local_step_bwd', dt, N, K, D, S, ptr(eta1), ptr(eta2_diag), ptr(eta1_phi2), ptr(L_raw),
               ptr(pi_raw), ptr(phi_rec), ptr(theta_rec), int(den_mode), ptr(noise), int(seed) & 0xFFFFFFFFFFFFFFFF,
               ptr(log_r), ptr(gx), ptr(glr), float(greg), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
-              ptr(out[4]), ptr(work), nbytes, stream_ptr(dev))
-    return tuple(out)
+              ptr(out[4]), ptr(th_bar), ptr(work), nbytes, stream_ptr(dev))
+    return tuple(out) + ((th_bar,) if want_theta_rec_bar else ())
 
 
 def fill_noise(N, K, D, S, seed, dtype, device, want_noise=True, want_u=True):
@@ -227,6 +229,21 @@ def decoder_loglike(y, means, out2, w, mode):
     _lib.call('vmp_decoder_loglike', dt, N, K, S, Dobs, int(mode), ptr(y), ptr(means), ptr(out2), ptr(w), ptr(acc),
               stream_ptr(dev))
     return acc
+
+
+def decoder_loglike_backward(y, means, out2, w, mode, scale):
+    """(g_means, g_out2, g_w) = scale * d acc / d (means, out2, w) of `decoder_loglike`."""
+    N, K, S, Dobs = out2.shape
+    dt, dev = out2.dtype, out2.device
+    y = _chk(y, (N, Dobs), dt, 'y'); out2 = out2.contiguous(); w = _chk(w, (N, K), dt, 'weights')
+    g_means = None
+    if means is not None:
+        means = _chk(means, (N, K, S, Dobs), dt, 'means')
+        g_means = torch.empty_like(means)
+    g_out2, g_w = torch.empty_like(out2), torch.empty_like(w)
+    _lib.call('vmp_decoder_loglike_bwd', dt, N, K, S, Dobs, int(mode), ptr(y), ptr(means), ptr(out2), ptr(w),
+              float(scale), ptr(g_means), ptr(g_out2), ptr(g_w), stream_ptr(dev))
+    return g_means, g_out2, g_w
 
 
 def gaussian_logprob_nat(x, eta1, eta2, log_w=None, per_samp=False):

@@ -57,6 +57,60 @@ int decoder_loglike(int64_t N, int K, int S, int Dobs, int mode, const T* y, con
     return launch_status();
 }
 
+// Reverse of the weighted decoder reduction: with F = sum_{n,k,s,d} w_nk f(y, means, out2) (the forward accumulator),
+//   g_means = scale dF/dmeans, g_out2 = scale dF/dout2  [N,K,S,Dobs],  g_w = scale dF/dw  [N,K].
+// One warp per (n,k): it owns all S rows of the pair, so g_w needs no atomics; pure HBM stream.
+template <typename T>
+__global__ void __launch_bounds__(256)
+decoder_loglike_bwd_kernel(int64_t N, int K, int S, int Dobs, int mode, const T* __restrict__ y,
+                           const T* __restrict__ means, const T* __restrict__ out2, const T* __restrict__ w, T scale,
+                           T* __restrict__ g_means, T* __restrict__ g_out2, T* __restrict__ g_w) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t nk = warp; nk < N * K; nk += nwarps) {
+        const int64_t n = nk / K;
+        const T wk = w[nk] * scale;
+        const T* yr = y + n * Dobs;
+        T fsum = T(0);
+        for (int s = 0; s < S; ++s) {
+            const int64_t row = nk * S + s;
+            const T* o2 = out2 + row * Dobs;
+            if (mode == 0) {
+                const T* mu = means + row * Dobs;
+                for (int d = lane; d < Dobs; d += 32) {
+                    const T e = yr[d] - mu[d], v = o2[d], iv = T(1) / v;
+                    fsum += e * e * iv + t_log(v + T(1e-8));
+                    g_means[row * Dobs + d] = T(-2) * wk * e * iv;
+                    g_out2[row * Dobs + d] = wk * (T(1) / (v + T(1e-8)) - e * e * iv * iv);
+                }
+            } else {
+                for (int d = lane; d < Dobs; d += 32) {
+                    const T t = -o2[d] * yr[d];
+                    fsum -= t_softplus(t);
+                    g_out2[row * Dobs + d] = wk * yr[d] / (T(1) + t_exp(-t));     // y * sigmoid(-logit y)
+                }
+            }
+        }
+        fsum = warp_sum(fsum);
+        if (lane == 0 && g_w != nullptr) g_w[nk] = scale * fsum;
+    }
+}
+
+template <typename T>
+int decoder_loglike_bwd(int64_t N, int K, int S, int Dobs, int mode, const T* y, const T* means, const T* out2,
+                        const T* w, double scale, T* g_means, T* g_out2, T* g_w, void* stream) {
+    if (N < 0 || K <= 0 || S <= 0 || Dobs <= 0 || !y || !out2 || !w || !g_out2) return VMP_E_BADARG;
+    if (mode != 0 && mode != 1) return VMP_E_BADMODE;
+    if (mode == 0 && (!means || !g_means)) return VMP_E_BADARG;
+    if (N == 0) return VMP_OK;
+    int64_t grid = (N * K + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    decoder_loglike_bwd_kernel<T><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(N, K, S, Dobs, mode, y, means, out2,
+                                                                                    w, (T)scale, g_means, g_out2, g_w);
+    return launch_status();
+}
+
 // ---- general dense-natural-parameter Gaussian log density ---------------------------------------------------------
 // One thread per (n,k): P = -2 eta2 = L L^T (packed, local memory), mu = P^-1 eta1,
 //   log N(x) = -1/2 |L^T (x - mu)|^2 + sum log L_ii - D/2 log 2pi
@@ -151,6 +205,16 @@ int vmp_decoder_loglike_f32(int64_t N, int K, int S, int Dobs, int mode, const f
 int vmp_decoder_loglike_f64(int64_t N, int K, int S, int Dobs, int mode, const double* y, const double* means,
                             const double* out2, const double* w, double* acc, void* stream) {
     return vmp::decoder_loglike<double>(N, K, S, Dobs, mode, y, means, out2, w, acc, stream);
+}
+int vmp_decoder_loglike_bwd_f32(int64_t N, int K, int S, int Dobs, int mode, const float* y, const float* means,
+                                const float* out2, const float* w, double scale, float* g_means, float* g_out2,
+                                float* g_w, void* stream) {
+    return vmp::decoder_loglike_bwd<float>(N, K, S, Dobs, mode, y, means, out2, w, scale, g_means, g_out2, g_w, stream);
+}
+int vmp_decoder_loglike_bwd_f64(int64_t N, int K, int S, int Dobs, int mode, const double* y, const double* means,
+                                const double* out2, const double* w, double scale, double* g_means, double* g_out2,
+                                double* g_w, void* stream) {
+    return vmp::decoder_loglike_bwd<double>(N, K, S, Dobs, mode, y, means, out2, w, scale, g_means, g_out2, g_w, stream);
 }
 int vmp_gaussian_logprob_nat_f32(int64_t N, int K, int S, int D, const float* x, const float* eta1, const float* eta2,
                                  const float* log_w, float* out, void* stream) {

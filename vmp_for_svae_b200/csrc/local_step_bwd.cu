@@ -17,8 +17,10 @@
 namespace vmp {
 
 constexpr int BWD_MAX_D = 16;
+// per-component accumulator: P2_bar D^2 | h2_bar D | mu2_bar D | s_sum | W_bar D^2 | m_bar D | cden_bar
+__host__ __device__ inline int bwd_klen(int D) { return 2 * D * D + 3 * D + 2; }
 
-template <typename T, int DT>
+template <typename T, int DT, bool TH>
 __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, int Drt, int S, int PTS, int den_mode, const T* __restrict__ eta1,
                       const T* __restrict__ eta2d, const T* __restrict__ phi_rec, const T* __restrict__ theta_rec,
                       const T* __restrict__ noise, uint64_t seed, const T* __restrict__ log_r,
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, i
     for (int e = tid; e < PTS; e += blockDim.x) gsum[e] = T(0);
     __syncthreads();
 
-    const int plen = phi_record_len(D), tlen = theta_record_len(D), kl = D * D + 2 * D + 1;
+    const int plen = phi_record_len(D), tlen = theta_record_len(D), kl = bwd_klen(D);
     const T* prec = phi_rec + (size_t)k * plen;
     const T* P2 = prec;
     const T* trec = theta_rec + (size_t)k * tlen;
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, i
     T Lc[DM * DM], Li[DM * DM], Sg[DM * DM];      // L (lower), L^-1 (lower), Sig = P~^-1 (full)
     T p1[DM], mu1[DM], dv[DM], bv[DM], mut[DM], gmu[DM], Lb[DM * DM];
     T r = T(0), glrp = T(0), hldv = T(0);
+    T Wb[TH ? DM * DM : 1], mb[TH ? DM : 1];      // d/dW (lower), d/dm of the regulariser (Student-t theta is trained)
     if (act) {
 #pragma unroll
         for (int i = 0; i < D; ++i) {
@@ -115,6 +118,12 @@ __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, i
         }
 #pragma unroll
         for (int e = 0; e < D * D; ++e) Lb[e] = T(0);
+        if (TH) {
+#pragma unroll
+            for (int e = 0; e < D * D; ++e) Wb[e] = T(0);
+#pragma unroll
+            for (int i = 0; i < D; ++i) mb[i] = T(0);
+        }
         r = t_exp(log_r[n * K + k]);
         // samples: u_s, x_s, Gx_s, t_s ; accumulate gmu, L_bar, T
         T Tsum = T(0);
@@ -153,8 +162,17 @@ __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, i
                 T sacc = T(0);
 #pragma unroll
                 for (int c = i; c < D; ++c) sacc = fma(W[c * D + i], wx[c], sacc);
-                Gx[i] = gxs[i] + greg / T(S) * r * coef * sacc;
+                const T gden = greg / T(S) * r * coef * sacc;        // -greg r/S d den/d x
+                Gx[i] = gxs[i] + gden;
                 gmu[i] += Gx[i];
+                if (TH) mb[i] -= gden;
+            }
+            if (TH) {
+                const T cf = greg / T(S) * r * coef;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int c = 0; c <= i; ++c) Wb[i * D + c] = fma(cf * wx[i], mut[c] + u[c] - mth[c], Wb[i * D + c]);
             }
 #pragma unroll
             for (int i = 0; i < D; ++i) {                          // t = L^-1 Gx
@@ -258,6 +276,16 @@ __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, i
         atomicAdd(ka + D * D + D + i, (double)(-dbar[i]));
     }
     atomicAdd(ka + D * D + 2 * D, (double)s_bar);
+    if (TH) {
+        double* kt = ka + D * D + 2 * D + 1;
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int c = 0; c <= i; ++c) atomicAdd(kt + i * D + c, (double)Wb[i * D + c]);
+            atomicAdd(kt + D * D + i, (double)mb[i]);
+        }
+        atomicAdd(kt + D * D + D, (double)(-greg * r));
+    }
     }
     __syncthreads();
     for (int e = tid; e < npts * D; e += blockDim.x) {             // per-point results out of the shared accumulators
@@ -272,7 +300,8 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 local_step_bwd_epilogue_kernel(int K, int D, const T* __restrict__ eta1_phi2, const T* __restrict__ L_raw,
                                const T* __restrict__ pi_raw, const double* __restrict__ kacc,
-                               T* __restrict__ h2_bar, T* __restrict__ L_raw_bar, T* __restrict__ pi_raw_bar) {
+                               T* __restrict__ h2_bar, T* __restrict__ L_raw_bar, T* __restrict__ pi_raw_bar,
+                               T* __restrict__ theta_rec_bar) {
     extern __shared__ double sm[];
     const int ld = D + 1;
     double* L2 = sm;                 // D x ld
@@ -281,7 +310,7 @@ local_step_bwd_epilogue_kernel(int K, int D, const T* __restrict__ eta1_phi2, co
     double* Pb = Pi + D * ld;        // P2_bar (full)
     double* vec = Pb + D * ld;       // mu2 | w2 | mu2_bar
     double* red = vec + 3 * D;
-    const int k = blockIdx.x, kl = D * D + 2 * D + 1;
+    const int k = blockIdx.x, kl = bwd_klen(D);
     const double* ka = kacc + (size_t)k * kl;
     for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
         const int i = e / D, j = e % D;
@@ -336,6 +365,11 @@ local_step_bwd_epilogue_kernel(int K, int D, const T* __restrict__ eta1_phi2, co
         }
         L_raw_bar[(size_t)k * D * D + e] = (T)g;
     }
+    if (theta_rec_bar != nullptr) {                                   // W_bar | m_bar | cden_bar, 0, 0, 0
+        const int tlen = theta_record_len(D);
+        for (int e = threadIdx.x; e < tlen; e += blockDim.x)
+            theta_rec_bar[(size_t)k * tlen + e] = e < D * D + D + 1 ? (T)ka[D * D + 2 * D + 1 + e] : T(0);
+    }
     // pi_raw_bar = s_sum - softmax(pi_raw) * sum_k s_sum
     double mx = -CUDART_INF, tot = 0.0;
     for (int j = threadIdx.x; j < K; j += blockDim.x) mx = fmax(mx, (double)pi_raw[j]);
@@ -358,7 +392,7 @@ local_step_bwd_epilogue_kernel(int K, int D, const T* __restrict__ eta1_phi2, co
     if (threadIdx.x == 0) pi_raw_bar[k] = (T)(s_sum - exp((double)pi_raw[k] - mx) / bse * tot);
 }
 
-template <typename T, int DT>
+template <typename T, int DT, bool TH>
 static cudaError_t launch_bwd_main(int64_t N, int K, int D, int S, int den_mode, const T* eta1, const T* eta2d,
                                    const T* phi_rec, const T* theta_rec, const T* noise, uint64_t seed, const T* log_r,
                                    const T* gx, const T* glr, T greg, T* eta1_bar, T* eta2d_bar, double* kacc,
@@ -367,7 +401,7 @@ static cudaError_t launch_bwd_main(int64_t N, int K, int D, int S, int den_mode,
     const int threads = ((PTS * K + 31) / 32) * 32;
     const size_t smem = (size_t)PTS * 2 * D * sizeof(double) + (size_t)PTS * sizeof(T);
     const int64_t grid = (N + PTS - 1) / PTS;
-    local_step_bwd_kernel<T, DT><<<(unsigned)grid, threads, smem, st>>>(N, K, D, S, PTS, den_mode, eta1, eta2d, phi_rec,
+    local_step_bwd_kernel<T, DT, TH><<<(unsigned)grid, threads, smem, st>>>(N, K, D, S, PTS, den_mode, eta1, eta2d, phi_rec,
                                                                         theta_rec, noise, seed, log_r, gx, glr, greg,
                                                                         eta1_bar, eta2d_bar, kacc);
     return cudaGetLastError();
@@ -377,12 +411,12 @@ template <typename T>
 static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* eta1_phi2,
                                const T* L_raw, const T* pi_raw, const T* phi_rec, const T* theta_rec, int den_mode,
                                const T* noise, uint64_t seed, const T* log_r, const T* gx, const T* glr, double greg,
-                               T* eta1_bar, T* eta2d_bar, T* h2_bar, T* L_raw_bar, T* pi_raw_bar, void* work,
-                               size_t work_bytes, cudaStream_t st) {
+                               T* eta1_bar, T* eta2d_bar, T* h2_bar, T* L_raw_bar, T* pi_raw_bar,
+                               T* theta_rec_bar, void* work, size_t work_bytes, cudaStream_t st) {
     if (N < 0 || K < 1 || K > 256 || S < 1) return VMP_E_BADARG;
     if (D < 1 || D > BWD_MAX_D) return VMP_E_BADDIM;
     if (den_mode != VMP_DEN_GAUSS && den_mode != VMP_DEN_STUDENT) return VMP_E_BADMODE;
-    const size_t kl = (size_t)D * D + 2 * D + 1;
+    const size_t kl = (size_t)bwd_klen(D);
     if (!work || work_bytes < (size_t)K * kl * sizeof(double)) return VMP_E_BADARG;
     if (!eta1_phi2 || !L_raw || !pi_raw || !h2_bar || !L_raw_bar || !pi_raw_bar) return VMP_E_BADARG;
     double* kacc = static_cast<double*>(work);
@@ -393,22 +427,27 @@ static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, co
         cudaError_t e;
 #define VMP_BWD_CASE(DD)                                                                                              \
     case DD:                                                                                                          \
-        e = launch_bwd_main<T, DD>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise, seed, log_r, gx, glr, \
-                                   (T)greg, eta1_bar, eta2d_bar, kacc, st);                                           \
+        e = theta_rec_bar ? launch_bwd_main<T, DD, true>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,   \
+                                                         seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc, st)  \
+                          : launch_bwd_main<T, DD, false>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,  \
+                                                          seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc, st); \
         break;
         switch (D) {
             VMP_BWD_CASE(1) VMP_BWD_CASE(2) VMP_BWD_CASE(3) VMP_BWD_CASE(4) VMP_BWD_CASE(5) VMP_BWD_CASE(6)
             VMP_BWD_CASE(7) VMP_BWD_CASE(8)
             default:
-                e = launch_bwd_main<T, 0>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise, seed, log_r, gx,
-                                          glr, (T)greg, eta1_bar, eta2d_bar, kacc, st);
+                e = theta_rec_bar ? launch_bwd_main<T, 0, true>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,
+                                                                seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc, st)
+                                  : launch_bwd_main<T, 0, false>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,
+                                                                 seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc,
+                                                                 st);
         }
 #undef VMP_BWD_CASE
         if (e != cudaSuccess) return (int)e;
     }
     const size_t esm = (size_t)(4 * D * (D + 1) + 3 * D + 32) * sizeof(double);
     local_step_bwd_epilogue_kernel<T><<<K, 128, esm, st>>>(K, D, eta1_phi2, L_raw, pi_raw, kacc, h2_bar, L_raw_bar,
-                                                           pi_raw_bar);
+                                                           pi_raw_bar, theta_rec_bar);
     return launch_status();
 }
 
@@ -416,17 +455,17 @@ static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, co
 
 extern "C" {
 size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D) {
-    return (size_t)K * ((size_t)D * D + 2 * D + 1) * sizeof(double);
+    return (size_t)K * (size_t)vmp::bwd_klen(D) * sizeof(double);
 }
 int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                                 const float* eta1_phi2, const float* L_raw, const float* pi_raw, const float* phi_rec,
                                 const float* theta_rec, int den_mode, const float* noise, uint64_t seed,
                                 const float* log_r, const float* gx, const float* glr, double greg, float* eta1_bar,
                                 float* eta2_diag_bar, float* eta1_phi2_bar, float* L_raw_bar, float* pi_raw_bar,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                float* theta_rec_bar, void* workspace, size_t workspace_bytes, void* stream) {
     return vmp::svae_local_step_bwd<float>(N, K, D, S, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec,
                                            den_mode, noise, seed, log_r, gx, glr, greg, eta1_bar, eta2_diag_bar,
-                                           eta1_phi2_bar, L_raw_bar, pi_raw_bar, workspace, workspace_bytes,
+                                           eta1_phi2_bar, L_raw_bar, pi_raw_bar, theta_rec_bar, workspace, workspace_bytes,
                                            static_cast<cudaStream_t>(stream));
 }
 int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
@@ -434,10 +473,10 @@ int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* et
                                 const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
                                 uint64_t seed, const double* log_r, const double* gx, const double* glr, double greg,
                                 double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
-                                double* pi_raw_bar, void* workspace, size_t workspace_bytes, void* stream) {
+                                double* pi_raw_bar, double* theta_rec_bar, void* workspace, size_t workspace_bytes, void* stream) {
     return vmp::svae_local_step_bwd<double>(N, K, D, S, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec,
                                             den_mode, noise, seed, log_r, gx, glr, greg, eta1_bar, eta2_diag_bar,
-                                            eta1_phi2_bar, L_raw_bar, pi_raw_bar, workspace, workspace_bytes,
+                                            eta1_phi2_bar, L_raw_bar, pi_raw_bar, theta_rec_bar, workspace, workspace_bytes,
                                             static_cast<cudaStream_t>(stream));
 }
 }
