@@ -19,20 +19,21 @@ from . import core
 
 class _LocalStepFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, S, den_mode, seed, noise):
+    def forward(ctx, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, S, den_mode, seed, noise, u):
         eta1, eta2_diag = eta1.contiguous(), eta2_diag.contiguous()
         eta1_phi2, L_raw, pi_raw = eta1_phi2.contiguous(), L_raw.contiguous(), pi_raw.contiguous()
         phi_rec = core.phi_prepare(eta1_phi2, L_raw, pi_raw)
-        out = core.local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=den_mode, noise=noise, seed=seed,
-                              want_x_sample=False, want_z=False, materialize_x_k=True)
+        theta_rec = theta_rec.detach().contiguous()
+        out = core.local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=den_mode, noise=noise, u=u, seed=seed,
+                              want_x_sample=True, want_z=True, materialize_x_k=True)
         ctx.save_for_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, out['log_r'])
         ctx.noise, ctx.S, ctx.den_mode, ctx.seed = noise, S, den_mode, seed
         reg = out['elbo_acc'][2].to(eta1.dtype)
-        ctx.mark_non_differentiable(out['elbo_acc'])
-        return out['x_k_samples'], out['log_r'], reg, out['elbo_acc']
+        ctx.mark_non_differentiable(out['elbo_acc'], out['x_sample'], out['z'])
+        return out['x_k_samples'], out['log_r'], reg, out['elbo_acc'], out['x_sample'], out['z']
 
     @staticmethod
-    def backward(ctx, gx, glr, greg, _gacc):
+    def backward(ctx, gx, glr, greg, _gacc, _gxs, _gz):
         eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, log_r = ctx.saved_tensors
         N, D = eta1.shape
         K = phi_rec.shape[0]
@@ -43,16 +44,18 @@ class _LocalStepFn(torch.autograd.Function):
         g = core.local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, ctx.S, log_r, gx,
                                      glr, greg, den_mode=ctx.den_mode, noise=ctx.noise, seed=ctx.seed,
                                      want_theta_rec_bar=want_th)
-        return g[0], g[1], g[2], g[3], g[4], (g[5] if want_th else None), None, None, None, None
+        return g[0], g[1], g[2], g[3], g[4], (g[5] if want_th else None), None, None, None, None, None
 
 
 def local_step_autograd(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, S, den_mode=core.DEN_GAUSS, seed=0,
-                        noise=None):
-    """-> (x_k_samples[N,K,S,D], log_r[N,K], regulariser (0-d), elbo_acc[4] double, non-differentiable).
+                        noise=None, u=None, full=False):
+    """-> (x_k_samples[N,K,S,D], log_r[N,K], regulariser (0-d), elbo_acc[4] double, non-differentiable); with
+    full=True also the selected sample x[n, z_n, 0] [N,D] and z[N] of the same pass (inputs of the CVI M-step).
     theta_rec comes from core.theta_prepare_* (a constant of the graph for the GMM prior, as in the reference) or from
     `student_theta_record` below (differentiable: the SMM variant trains mu_k, L_k by gradient)."""
-    return _LocalStepFn.apply(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, int(S), int(den_mode), int(seed),
-                              noise)
+    out = _LocalStepFn.apply(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, int(S), int(den_mode), int(seed),
+                             noise, u)
+    return out if full else out[:4]
 
 
 def student_theta_record(alpha_nat, mu_k, L_k_raw, dof):
