@@ -206,6 +206,19 @@ int vmp_decoder_loglike_bwd_f64(int64_t N, int K, int S, int Dobs, int mode, con
                                 const double* out2, const double* w, double scale, double* g_means, double* g_out2,
                                 double* g_w, void* stream);
 
+/* Test-time metrics over the decoder outputs (losses.py): one pass yields, per (n,k),
+ *   sq[n,k]  = 1/S sum_s sum_d m_d (target_nd - means_nksd)^2   -> losses.weighted_mse (9-40), imputation_mse (147-170)
+ *   lse[n,k] = log sum_s exp(log_w_nks + sum_d m_d log p(y_nd | means_nksd, out2_nksd))
+ *              -> losses.diagonal_gaussian_logprob (83-144, mode 0: out2 = variances), bernoulli_logprob (43-80, mode 1:
+ *                 out2 = logits).  mask[N,Dobs] uint8 (1 = counted; NULL = all), target NULL = y, log_w_nks[N,K,S] NULL = 0;
+ * sq / lse may be NULL.  The K-sized tail (weights, log-sum-exp over k, mean over n) is left to the caller.       */
+int vmp_decoder_metrics_f32(int64_t N, int K, int S, int Dobs, int mode, const float* y, const float* target,
+                            const float* means, const float* out2, const uint8_t* mask, const float* log_w_nks,
+                            float* sq, float* lse, void* stream);
+int vmp_decoder_metrics_f64(int64_t N, int K, int S, int Dobs, int mode, const double* y, const double* target,
+                            const double* means, const double* out2, const uint8_t* mask, const double* log_w_nks,
+                            double* sq, double* lse, void* stream);
+
 /* General dense-natural-parameter Gaussian log-density (API surface of distributions/gaussian.py).
  * S == 0: gaussian.log_probability_nat (gaussian.py:30-71): x[N,D], eta1[N,K,D], eta2[N,K,D,D], log_w[K] or NULL
  *         -> out[N,K] normalised over K.   S >= 1: gaussian.log_probability_nat_per_samp (74-105):

@@ -54,3 +54,27 @@ def regen_decoder(g):
 
 
 SVAE_CASES = ['svae_c1', 'svae_c2', 'svae_init', 'svae_d8', 'svae_d16', 'svae_d32', 'svae_d64']
+
+
+def losses_inputs(seed, N, K, S, D, C=4):
+    """Same seeded inputs as tests/golden/make_golden.py::losses_inputs."""
+    rs = np.random.RandomState(seed)
+    y = rs.randn(N, D)
+    pred = y[:, None, None, :] + 0.7 * rs.randn(N, K, S, D)
+    var = np.exp(0.4 * rs.randn(N, K, S, D))
+    logits = 1.5 * rs.randn(N, K, S, D)
+    r = rs.dirichlet(0.5 * np.ones(K), N)
+    labels = rs.randint(0, C, N)
+    return y, pred, var, logits, r, labels
+
+
+def imputation_stub(N, K, S, D):
+    """Same deterministic stand-in for svae.inference as make_golden.py::imputation_stub (numpy in, numpy out)."""
+    cnt = [0]
+
+    def imp(y_pert):
+        rs = np.random.RandomState(500 + cnt[0])
+        cnt[0] += 1
+        means = y_pert[:, None, None, :] + 0.3 * rs.randn(N, K, S, D)
+        return means, np.exp(0.3 * rs.randn(N, K, S, D)), np.log(rs.dirichlet(np.ones(K), N))
+    return imp

@@ -250,9 +250,69 @@ def distribution_cases(tf, M):
     print('distributions ok')
 
 
+def losses_inputs(seed, N, K, S, D, C=4):
+    """Seeded inputs of the losses fixtures; tests regenerate them (nothing large is stored)."""
+    rs = np.random.RandomState(seed)
+    y = rs.randn(N, D)
+    pred = y[:, None, None, :] + 0.7 * rs.randn(N, K, S, D)
+    var = np.exp(0.4 * rs.randn(N, K, S, D))
+    logits = 1.5 * rs.randn(N, K, S, D)
+    r = rs.dirichlet(0.5 * np.ones(K), N)
+    labels = rs.randint(0, C, N)
+    return y, pred, var, logits, r, labels
+
+
+def imputation_stub(N, K, S, D):
+    """Deterministic stand-in for svae.inference inside imputation_losses: call c -> (means, vars/logits, log r)."""
+    cnt = [0]
+
+    def imp(y_pert):
+        rs = np.random.RandomState(500 + cnt[0])
+        cnt[0] += 1
+        means = y_pert[:, None, None, :] + 0.3 * rs.randn(N, K, S, D)
+        return means, np.exp(0.3 * rs.randn(N, K, S, D)), np.log(rs.dirichlet(np.ones(K), N))
+    return imp
+
+
+def losses_cases(tf, M):
+    import importlib
+    losses = importlib.import_module('losses')
+    N, K, S, D, P = 23, 4, 5, 6, 3
+    y, pred, var, logits, r, labels = losses_inputs(77, N, K, S, D)
+    c = tf.constant
+    yb = np.sign(y)
+    out = dict(N=N, K=K, S=S, D=D, P=P, seed=77)
+    out['weighted_mse'] = A(losses.weighted_mse(c(y), c(pred), c(r)))
+    out['gauss_logprob'] = A(losses.diagonal_gaussian_logprob(c(y), c(pred), c(var), c(np.log(r))))
+    lw3 = np.log(r)[:, :, None] + 0.1 * np.random.RandomState(3).randn(N, K, S)
+    out['gauss_logprob_nks'] = A(losses.diagonal_gaussian_logprob(c(y), c(pred), c(var), c(lw3)))
+    mask = A(losses.generate_missing_data_mask(c(y), 0.3, seed=0))
+    out['mask'] = mask
+    out['gauss_logprob_mask'] = A(losses.diagonal_gaussian_logprob(c(y), c(pred), c(var), c(np.log(r)), mask=c(mask)))
+    out['bernoulli_logprob'] = A(losses.bernoulli_logprob(c(yb), c(logits), c(np.log(r))))
+    out['bernoulli_logprob_mask'] = A(losses.bernoulli_logprob(c(yb), c(logits), c(np.log(r)), c(mask)))
+    out['imputation_mse'] = A(losses.imputation_mse(c(y), c(pred), c(r), c(mask)))
+    ent, pur = losses.purity(c(r), c(np.eye(4)[labels]))
+    out['entropy'], out['purity'] = A(ent), A(pur)
+    for dt, yy in (('standard', y), ('bernoulli', yb)):
+        del tf.rng_log[:]
+        stub = imputation_stub(N, K, S, D)
+        mse, ll = losses.imputation_losses(c(yy), c(mask), lambda yp: tuple(c(t) for t in stub(A(yp))), P, S, seed=0,
+                                           decoder_type=dt)
+        log = take_log(tf)
+        assert len(log) == P and all(k == 'random_normal' for k, _ in log)   # perturb_data is always Gaussian noise
+        out['imp_noise'] = np.stack([v for _, v in log])
+        out['imp_mse_' + dt], out['imp_ll_' + dt] = A(mse), A(ll)
+    np.savez_compressed(os.path.join(HERE, 'losses.npz'), **out)
+    print('losses', {k: float(v) for k, v in out.items() if np.ndim(v) == 0 and k not in 'NKSDP'})
+
+
 if __name__ == '__main__':
     tf, M = import_reference()
     tf.set_float(np.float64)
+    if '--losses-only' in sys.argv:
+        losses_cases(tf, M)
+        sys.exit(0)
     svae_case(tf, M, 'svae_c1', K=10, D=2, N=100, S=10, seed=0, rho=0.1)
     svae_case(tf, M, 'svae_c2', K=10, D=6, N=274, S=10, seed=0, rho=0.2, dobs=6, keep_big=False)
     svae_case(tf, M, 'svae_init', K=10, D=2, N=37, S=2, seed=3, rho=0.1, perturb=False)
@@ -263,3 +323,4 @@ if __name__ == '__main__':
     svae_smm_case(tf, M, 'svae_smm', K=6, D=3, N=41, S=4, seed=0, rho=0.1, dof=5.0)
     mixture_cases(tf, M)
     distribution_cases(tf, M)
+    losses_cases(tf, M)

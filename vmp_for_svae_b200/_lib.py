@@ -32,6 +32,7 @@ _SIGS_T = {
     'vmp_decoder_loglike': [c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_decoder_loglike_bwd': [c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr,
                                 c_ptr, c_ptr],
+    'vmp_decoder_metrics': [c_i64, c_int, c_int, c_int, c_int] + [c_ptr] * 8 + [c_ptr],
     'vmp_gaussian_logprob_nat': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
 }
 _SIGS = {

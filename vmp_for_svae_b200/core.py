@@ -246,6 +246,24 @@ def decoder_loglike_backward(y, means, out2, w, mode, scale):
     return g_means, g_out2, g_w
 
 
+def decoder_metrics(y, means, out2, mode, target=None, mask=None, log_w_nks=None, want_sq=True, want_lse=True):
+    """(sq[N,K], lse[N,K]) of vmp_decoder_metrics (see include/vmp_svae.h); mode 0 gaussian, 1 bernoulli."""
+    N, K, S, Dobs = out2.shape
+    dt, dev = out2.dtype, out2.device
+    y = _chk(y, (N, Dobs), dt, 'y'); out2 = out2.contiguous(); means = _chk(means, (N, K, S, Dobs), dt, 'means')
+    if target is not None:
+        target = _chk(target, (N, Dobs), dt, 'target')
+    if mask is not None:
+        mask = _chk(mask.to(torch.uint8), (N, Dobs), torch.uint8, 'missing_data_mask')
+    if log_w_nks is not None:
+        log_w_nks = _chk(log_w_nks, (N, K, S), dt, 'log_weights')
+    sq = torch.empty(N, K, dtype=dt, device=dev) if want_sq else None
+    lse = torch.empty(N, K, dtype=dt, device=dev) if want_lse else None
+    _lib.call('vmp_decoder_metrics', dt, N, K, S, Dobs, int(mode), ptr(y), ptr(target), ptr(means), ptr(out2), ptr(mask),
+              ptr(log_w_nks), ptr(sq), ptr(lse), stream_ptr(dev))
+    return sq, lse
+
+
 def gaussian_logprob_nat(x, eta1, eta2, log_w=None, per_samp=False):
     N, K, D = eta1.shape
     dt, dev = eta1.dtype, eta1.device

@@ -111,6 +111,67 @@ int decoder_loglike_bwd(int64_t N, int K, int S, int Dobs, int mode, const T* y,
     return launch_status();
 }
 
+// ---- test-time metrics over the decoder outputs (losses.py) ----------------------------------------------------------
+// One warp per (n,k) streams its S rows once and produces both reductions the reference's metrics are built from:
+//   sq[n,k]  = 1/S sum_s sum_d m_d (t_nd - means_nksd)^2                       (weighted_mse, imputation_mse)
+//   lse[n,k] = log sum_s exp( lw_nks + sum_d m_d log p(y_nd | means, out2) )   (diagonal_gaussian_logprob, bernoulli_logprob)
+// m = missing-data mask (NULL = all ones), t = the MSE target (NULL = y), lw = per-sample log weights (NULL = 0).
+template <typename T>
+__global__ void __launch_bounds__(256)
+decoder_metrics_kernel(int64_t N, int K, int S, int Dobs, int mode, const T* __restrict__ y, const T* __restrict__ tgt,
+                       const T* __restrict__ means, const T* __restrict__ out2, const uint8_t* __restrict__ mask,
+                       const T* __restrict__ lw, T* __restrict__ sq, T* __restrict__ lse) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t nk = warp; nk < N * K; nk += nwarps) {
+        const int64_t n = nk / K;
+        const T* yr = y + n * Dobs;
+        const T* tr = (tgt != nullptr ? tgt : y) + n * Dobs;
+        const uint8_t* mr = mask != nullptr ? mask + n * Dobs : nullptr;
+        T sqs = T(0), mx = -CUDART_INF_F, acc = T(0);
+        for (int s = 0; s < S; ++s) {
+            const int64_t row = nk * S + s;
+            const T* mu = means + row * Dobs;
+            const T* o2 = out2 + row * Dobs;
+            T se = T(0), lp = T(0);
+            for (int d = lane; d < Dobs; d += 32) {
+                if (mr != nullptr && !mr[d]) continue;
+                const T e = tr[d] - mu[d];
+                se = fma(e, e, se);
+                if (mode == 0) {
+                    const T ey = yr[d] - mu[d], v = o2[d];
+                    lp -= T(0.5) * (ey * ey / v + t_log(v) + T(VMP_LOG_2PI));
+                } else {
+                    lp -= t_softplus(-o2[d] * yr[d]);
+                }
+            }
+            se = warp_sum(se);
+            lp = warp_sum(lp) + (lw != nullptr ? lw[row] : T(0));
+            sqs += se;
+            if (lp > mx) { acc = acc * t_exp(mx - lp) + T(1); mx = lp; }        // online log-sum-exp over samples
+            else acc += t_exp(lp - mx);
+        }
+        if (lane == 0) {
+            if (sq != nullptr) sq[nk] = sqs / T(S);
+            if (lse != nullptr) lse[nk] = mx + t_log(acc);
+        }
+    }
+}
+
+template <typename T>
+int decoder_metrics(int64_t N, int K, int S, int Dobs, int mode, const T* y, const T* tgt, const T* means, const T* out2,
+                    const uint8_t* mask, const T* lw, T* sq, T* lse, void* stream) {
+    if (N < 0 || K <= 0 || S <= 0 || Dobs <= 0 || !y || !means || !out2) return VMP_E_BADARG;
+    if (mode != 0 && mode != 1) return VMP_E_BADMODE;
+    if (N == 0) return VMP_OK;
+    int64_t grid = (N * K + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    decoder_metrics_kernel<T><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(N, K, S, Dobs, mode, y, tgt, means, out2,
+                                                                                mask, lw, sq, lse);
+    return launch_status();
+}
+
 // ---- general dense-natural-parameter Gaussian log density ---------------------------------------------------------
 // One thread per (n,k): P = -2 eta2 = L L^T (packed, local memory), mu = P^-1 eta1,
 //   log N(x) = -1/2 |L^T (x - mu)|^2 + sum log L_ii - D/2 log 2pi
@@ -215,6 +276,16 @@ int vmp_decoder_loglike_bwd_f64(int64_t N, int K, int S, int Dobs, int mode, con
                                 const double* out2, const double* w, double scale, double* g_means, double* g_out2,
                                 double* g_w, void* stream) {
     return vmp::decoder_loglike_bwd<double>(N, K, S, Dobs, mode, y, means, out2, w, scale, g_means, g_out2, g_w, stream);
+}
+int vmp_decoder_metrics_f32(int64_t N, int K, int S, int Dobs, int mode, const float* y, const float* target,
+                            const float* means, const float* out2, const uint8_t* mask, const float* log_w_nks,
+                            float* sq, float* lse, void* stream) {
+    return vmp::decoder_metrics<float>(N, K, S, Dobs, mode, y, target, means, out2, mask, log_w_nks, sq, lse, stream);
+}
+int vmp_decoder_metrics_f64(int64_t N, int K, int S, int Dobs, int mode, const double* y, const double* target,
+                            const double* means, const double* out2, const uint8_t* mask, const double* log_w_nks,
+                            double* sq, double* lse, void* stream) {
+    return vmp::decoder_metrics<double>(N, K, S, Dobs, mode, y, target, means, out2, mask, log_w_nks, sq, lse, stream);
 }
 int vmp_gaussian_logprob_nat_f32(int64_t N, int K, int S, int D, const float* x, const float* eta1, const float* eta2,
                                  const float* log_w, float* out, void* stream) {

@@ -21,6 +21,8 @@ import torch
 
 from . import core
 from .autograd import decoder_loglike_autograd, local_step_autograd, student_theta_record
+from .losses import (bernoulli_logprob, diagonal_gaussian_logprob, generate_missing_data_mask, imputation_losses, purity,
+                     weighted_mse)
 from .models import svae
 
 
@@ -130,34 +132,6 @@ class ResNet(torch.nn.Module):
         return (raw1 + res).reshape(*lead, self.out_dim), (a * sp(raw2) + a * sp(self.b2)).reshape(*lead, self.out_dim)
 
 
-# ------------------------------------------------------------------------------------------------ metrics (losses.py)
-def weighted_mse(y_true, y_pred, r_nk):
-    """losses.py:9-40."""
-    mse = ((y_true.unsqueeze(1).unsqueeze(2) - y_pred) ** 2).sum(3).mean(2)
-    return (mse * r_nk).sum(1).mean()
-
-
-def diagonal_gaussian_logprob(y, means, vars_, log_weights):
-    """losses.py:83-130 (weighted branch): mean_n log 1/S sum_s sum_k r_nk N(y_n | mean_nks, var_nks)."""
-    S = means.shape[2]
-    yy = y.unsqueeze(1).unsqueeze(2)
-    lp = (-0.5 * math.log(2 * math.pi) - 0.5 * torch.log(vars_) - 0.5 * (yy - means) ** 2 / vars_).sum(-1)
-    lp = torch.logsumexp(lp + log_weights.unsqueeze(2), dim=1)
-    return (torch.logsumexp(lp, dim=-1) - math.log(S)).mean()
-
-
-def purity(r_nk, labels, eps=1e-10):
-    """losses.py:313-349 : responsibility-weighted cluster entropy (0 = perfect) and purity (1 = perfect);
-    labels are class indices [N] (the reference takes the one-hot matrix)."""
-    N, K = r_nk.shape
-    onehot = torch.nn.functional.one_hot(labels.long(), int(labels.max()) + 1).to(r_nk.dtype)
-    N_kc = r_nk.t() @ onehot
-    N_k = r_nk.sum(0)
-    p_kc = N_kc / (N_k + eps).unsqueeze(1)
-    ent_k = -(p_kc * torch.log(p_kc + eps)).sum(1)
-    return float((N_k / N * ent_k).sum()), float((N_k / N * p_kc.max(1).values).sum())
-
-
 # ------------------------------------------------------------------------------------------------ the loop
 class SVAETrainer(object):
     """State + one-iteration step of the reference's training graph for config['method'] in
@@ -226,15 +200,33 @@ class SVAETrainer(object):
 
     @torch.no_grad()
     def evaluate(self, y, labels=None, nb_samples=100, seed=12345):
-        """experiments.py:262-304 : test-time inference with S=100 -> mse, log-likelihood, (entropy, purity)."""
+        """experiments.py:262-304 : test-time inference with S=100 -> mse, log-likelihood, (entropy, purity);
+        labels are class indices."""
         rec, x_k, log_r, reg, acc, _, _ = self.forward(y, nb_samples, seed, train=False)
         means, out2 = rec
         out = dict(mse=float(weighted_mse(y, means, torch.exp(log_r))))
         if self.decoder_type == 'standard':
             out['loli'] = float(diagonal_gaussian_logprob(y, means, out2, log_r))
+        else:
+            out['loli'] = float(bernoulli_logprob(y, out2, log_r))
         if labels is not None:
-            out['entropy'], out['purity'] = purity(torch.exp(log_r), labels)
+            onehot = torch.nn.functional.one_hot(labels.long(), int(labels.max()) + 1)
+            ent, pur = purity(torch.exp(log_r), onehot)
+            out['entropy'], out['purity'] = float(ent), float(pur)
         return out
+
+    @torch.no_grad()
+    def imputation(self, y, ratio_missing_data=0.1, nb_samples_pert=20, nb_samples=100, seed=0):
+        """experiments.py:361-377 : missing-data imputation through svae.inference -> (imp_mse, imp_logprob)."""
+        mask = generate_missing_data_mask(y, ratio_missing_data, seed=seed)
+        cnt = [0]
+
+        def impute(y_perturbed):
+            cnt[0] += 1
+            rec, _, log_r, _, _, _, _ = self.forward(y_perturbed.contiguous(), nb_samples, seed * 7919 + cnt[0], train=False)
+            return rec[0], rec[1], log_r
+        mse, ll = imputation_losses(y, mask, impute, nb_samples_pert, nb_samples, seed=seed, decoder_type=self.decoder_type)
+        return float(mse), float(ll)
 
 
 def run_experiment(config, nb_iters=2000, size_minibatch=64, measurement_freq=500, device='cuda', verbose=True,
@@ -257,6 +249,8 @@ def run_experiment(config, nb_iters=2000, size_minibatch=64, measurement_freq=50
             ev.update(iter=i, neg_elbo_normed=-float(out['elbo']) / size_minibatch, sec=time.time() - t0,
                       neg_rec=float(out['neg_rec']), reg=float(out['reg']), lrcvi=tr.lrcvi(),
                       bad_pivots=float(out['bad_pivots']))
+            if i == nb_iters - 1:
+                ev['imp_mse'], ev['imp_logprob'] = tr.imputation(y_te, nb_samples=nb_samples_te)
             hist.append(ev)
             if verbose:
                 print('Iteration %5d\t%.2fs\t-elbo/M %.4f\tmse_te %.4f\tloli_te %.4f\tpurity %.3f' % (
