@@ -53,3 +53,54 @@ def test_one_step_matches_oracle_graph():
     assert abs(float(elbo) - float(elbo_o)) < 1e-8 * abs(float(elbo_o))
     for a, b in zip(got, ref):
         assert float((a.cpu() - b).abs().max()) <= 1e-7 * max(float(b.abs().max()), 1e-6)
+
+
+@pytest.mark.parametrize('smm', [False, True], ids=['gmm', 'smm'])
+def test_dropin_surface_is_differentiable(smm):
+    """The reference-shaped calls svae.inference + svae.compute_elbo(_smm) + (-elbo).backward() (experiments.py:208-232)
+    give the oracle graph's gradients on encoder, decoder, phi_gmm (and mu_k, L_k of the SMM variant)."""
+    import copy
+    import numpy as np
+    from oracle import backward as ob, svae_port as sp
+    from vmp_for_svae_b200 import core, experiments as ex
+    from vmp_for_svae_b200.models import svae
+    dev = 'cuda:0'
+    N, K, D, S, Do = 40, 5, 3, 2, 4
+    cfg = dict(dataset='pinwheel', method='svae-cvi-smm' if smm else 'svae-cvi', lr=0.01, lrcvi=0.1, K=K, L=D, U=16,
+               DoF=5, seed=2)
+    tr = ex.SVAETrainer(cfg, obs_dim=Do, device=dev, nb_samples=S, stddev_init_nn=0.3)
+    tr.encoder.double(); tr.decoder.double()
+    phi_gmm = [torch.nn.Parameter(p.detach().double()) for p in tr.phi_gmm]
+    if smm:
+        theta = (tr.alpha.double(), torch.nn.Parameter(tr.mu_k.detach().double()),
+                 torch.nn.Parameter(tr.L_k.detach().double()), tr.dof.double())
+        extra = [theta[1], theta[2]]
+    else:
+        theta, extra = [t.double() for t in tr.theta], []
+    y = torch.as_tensor(np.random.RandomState(1).randn(N, Do) * 2.0, dtype=torch.float64, device=dev)
+    noise, _ = core.fill_noise(N, K, D, S, 5, torch.float64, dev, want_u=False)
+    y_rec, _, x_k, x_samples, log_z, _, phi_tilde = svae.inference(y, phi_gmm, tr.encoder, tr.decoder, nb_samples=S,
+                                                                   seed=0, noise=noise)
+    fn = svae.compute_elbo_smm if smm else svae.compute_elbo
+    elbo, details = fn(y, y_rec, theta, phi_tilde, x_k, log_z, 'standard')
+    params = list(tr.encoder.parameters()) + list(tr.decoder.parameters()) + phi_gmm + extra
+    got = torch.autograd.grad(-elbo, params)
+    assert x_samples.shape == (N, D) and not x_samples.requires_grad
+    # oracle graph
+    enc, dec = copy.deepcopy(tr.encoder).cpu(), copy.deepcopy(tr.decoder).cpu()
+    phi = [p.detach().cpu().clone().requires_grad_(True) for p in phi_gmm]
+    if smm:
+        th = [t.detach().cpu().clone() for t in theta]
+        th[1].requires_grad_(True); th[2].requires_grad_(True)
+        W, m, cden, nu = ob.theta_consts_student(th)
+        oextra = [th[1], th[2]]
+    else:
+        (W, m, cden), nu, oextra = ob.theta_consts_gauss([t.cpu() for t in theta]), None, []
+    e1, e2 = enc(y.cpu())
+    xo, lro, rego = ob.forward(e1, e2, phi[0], phi[1], phi[2], W, m, cden, noise.cpu(), nu=nu)
+    means, vars_ = dec(xo)
+    elbo_o = sp.expected_diagonal_gaussian_loglike(y.cpu(), means, vars_, weights=torch.exp(lro)) - rego
+    ref = torch.autograd.grad(-elbo_o, list(enc.parameters()) + list(dec.parameters()) + phi + oextra)
+    assert abs(float(elbo.detach()) - float(elbo_o.detach())) < 1e-8 * abs(float(elbo_o.detach()))
+    for a, b in zip(got, ref):
+        assert float((a.cpu() - b).abs().max()) <= 1e-7 * max(float(b.abs().max()), 1e-6)

@@ -109,15 +109,27 @@ def e_step(phi_enc, phi_gmm, nb_samples, seed=0, name="e_step", *, noise=None, u
     K, L2 = eta1_phi2.shape
     assert L2 == D
     assert tuple(L_k_raw.shape) == (K, D, D)
-    phi_rec = core.phi_prepare(eta1_phi2, L_k_raw, pi_k_raw)
-    out = core.local_step(eta1_phi1, eta2_phi1_diag, phi_rec, _zero_theta_rec(K, D, eta1_phi1), int(nb_samples),
-                          noise=noise, u=u, seed=seed, want_x_sample=False, want_z=False,
-                          materialize_x_k=bool(materialize))
+    leaves = (eta1_phi1, eta2_phi1_diag, eta1_phi2, L_k_raw, pi_k_raw)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in leaves) and materialize:
+        # training graph: the same forward kernel behind torch.autograd (reverse pass: csrc/local_step_bwd.cu)
+        from ..autograd import local_step_autograd
+        x_k, log_r, _, acc = local_step_autograd(*leaves, _zero_theta_rec(K, D, eta1_phi1), int(nb_samples), seed=seed,
+                                                 noise=noise, u=u)
+        phi_rec = core.phi_prepare(eta1_phi2.detach(), L_k_raw.detach(), pi_k_raw.detach())
+        out = dict(x_k_samples=x_k, log_r=log_r, elbo_acc=acc)
+    else:
+        leaves = None
+        phi_rec = core.phi_prepare(eta1_phi2, L_k_raw, pi_k_raw)
+        out = core.local_step(eta1_phi1, eta2_phi1_diag, phi_rec, _zero_theta_rec(K, D, eta1_phi1), int(nb_samples),
+                              noise=noise, u=u, seed=seed, want_x_sample=False, want_z=False,
+                              materialize_x_k=bool(materialize))
     if float(out['elbo_acc'][3]) != 0.0:
         raise RuntimeError('Cholesky decomposition was not successful. The input might not be valid.')
     eta2_phi2 = -0.5 * phi_rec[:, :D * D].reshape(K, D, D)
-    phi_tilde = PhiTilde((eta1_phi1, eta2_phi1_diag), eta1_phi2, eta2_phi2, phi_rec)
+    phi_tilde = PhiTilde((eta1_phi1.detach(), eta2_phi1_diag.detach()), eta1_phi2.detach(), eta2_phi2, phi_rec)
     phi_tilde.seed, phi_tilde.noise = seed, noise
+    # autograd bookkeeping: compute_elbo re-enters the fused step with theta to get a differentiable regulariser
+    phi_tilde.leaves, phi_tilde.x_k, phi_tilde.S = leaves, out['x_k_samples'], int(nb_samples)
     return out['x_k_samples'], out['log_r'], phi_tilde, _LazyDbg(phi_tilde)
 
 
@@ -212,6 +224,12 @@ def update_gmm_params(current_gmm_params, gmm_params_star, step_size, name='cvi_
 def _neg_reconstruction_error(y, reconstructions, r_nk, decoder_type):
     means, out_2 = reconstructions
     N, K, S, Dobs = out_2.shape
+    if decoder_type not in ('standard', 'bernoulli'):
+        raise NotImplementedError
+    if torch.is_grad_enabled() and (out_2.requires_grad or r_nk.requires_grad or
+                                    (means is not None and means.requires_grad)):
+        from ..autograd import decoder_loglike_autograd
+        return decoder_loglike_autograd(y, reconstructions, r_nk, decoder_type)
     if decoder_type == 'standard':
         acc = core.decoder_loglike(y, means, out_2, r_nk, 0)               # vae.py:226-248
         return (-0.5 * acc / S - N * Dobs / 2.0 * math.log(2.0 * math.pi)).to(out_2.dtype)[0]
@@ -224,6 +242,15 @@ def _neg_reconstruction_error(y, reconstructions, r_nk, decoder_type):
 def _regulariser(theta_rec, den_mode, phi_tilde, x_k_samps, log_z_given_y_phi):
     N, K, S, L = x_k_samps.shape
     dt = x_k_samps.dtype
+    if isinstance(phi_tilde, PhiTilde) and getattr(phi_tilde, 'leaves', None) is not None and torch.is_grad_enabled():
+        # differentiable regulariser: the fused step again, now with theta (total derivative w.r.t. the leaves of
+        # e_step; the samples are regenerated from the same noise, so x_k_samps must be e_step's own output)
+        if x_k_samps is not phi_tilde.x_k:
+            raise ValueError('under autograd compute_elbo needs the x_k_samples returned by e_step/inference')
+        from ..autograd import local_step_autograd
+        _, _, reg, acc = local_step_autograd(*phi_tilde.leaves, theta_rec, S, den_mode=den_mode, seed=phi_tilde.seed,
+                                             noise=phi_tilde.noise)
+        return reg, acc[0].to(dt), acc[1].to(dt)
     if isinstance(phi_tilde, PhiTilde):
         eta1, eta2_diag = phi_tilde.phi_enc
         out = core.local_step(eta1, eta2_diag, phi_tilde.phi_rec, theta_rec, S, den_mode=den_mode,
@@ -261,7 +288,11 @@ def compute_elbo(y, reconstructions, theta, phi_tilde, x_k_samps, log_z_given_y_
 
 def compute_elbo_smm(y, reconstructions, theta, phi_tilde, x_k_samps, log_z_given_y_phi, decoder_type):
     """svae.py:265-322 ; theta = (alpha_nat, mu_k, L_k_raw, DoF) (experiments.py:174)."""
-    theta_rec = core.theta_prepare_student(theta)
+    if torch.is_grad_enabled() and (theta[1].requires_grad or theta[2].requires_grad):
+        from ..autograd import student_theta_record             # mu_k, L_k are trained by gradient (experiments.py:154-174)
+        theta_rec = student_theta_record(theta[0], theta[1], theta[2], theta[3])
+    else:
+        theta_rec = core.theta_prepare_student(theta)
     r_nk = torch.exp(log_z_given_y_phi)
     neg_rec = _neg_reconstruction_error(y, reconstructions, r_nk, decoder_type)
     reg, num, den = _regulariser(theta_rec, core.DEN_STUDENT, phi_tilde, x_k_samps, log_z_given_y_phi)
