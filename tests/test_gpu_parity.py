@@ -241,6 +241,46 @@ def test_group_engine_equals_generic_kernels(shape, tma, monkeypatch):
     assert float(out['elbo_acc'][3]) == 0.0
 
 
+@pytest.mark.parametrize('shape', [(203, 11, 64, 2), (37, 5, 64, 1), (1, 3, 64, 3)], ids=lambda s: 'N%dK%dD%dS%d' % s)
+@pytest.mark.parametrize('student', [False, True], ids=['gauss', 'student'])
+def test_2d_engine_equals_generic_kernels(shape, student, monkeypatch):
+    """The 2-D cyclic group engine (local_step_fast2d.cuh, D = 64) against the generic thread-per-pair kernels on the
+    same in-kernel noise stream, and on injected noise / Gumbel uniforms."""
+    from vmp_for_svae_b200 import core
+    N, K, D, S = shape
+    dt = torch.float32
+    prior, theta, phi_gmm, phi_enc, noise, u = _oracle_inputs(N, K, D, S, seed=D + N, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    pe, pg, th = dev(phi_enc), dev(phi_gmm), dev(theta)
+    phi_rec = core.phi_prepare(*pg)
+    if student:
+        rs = np.random.RandomState(3)
+        ths = [th[0], T(rs.randn(K, D)).to(DEV, dt), (T(0.3 / D ** 0.5 * rs.randn(K, D, D)) + torch.eye(D, dtype=torch.float64)).to(DEV, dt).contiguous(),
+               T(3.0 + 5.0 * rs.rand(K)).to(DEV, dt)]
+        theta_rec, den = core.theta_prepare_student(ths), core.DEN_STUDENT
+    else:
+        theta_rec, den = core.theta_prepare_gauss(th), core.DEN_GAUSS
+    for kw in (dict(seed=77), dict(noise=noise.to(DEV, dt).contiguous(), u=u.to(DEV, dt).contiguous())):
+        monkeypatch.setenv('VMP_FORCE_GENERIC', '1')
+        ref = core.local_step(pe[0], pe[1], phi_rec, theta_rec, S, den_mode=den, materialize_x_k=True, **kw)
+        monkeypatch.setenv('VMP_FORCE_GENERIC', '0')
+        monkeypatch.setenv('VMP_FAST_2D', '1')
+        out = core.local_step(pe[0], pe[1], phi_rec, theta_rec, S, den_mode=den, materialize_x_k=True, **kw)
+        torch.cuda.synchronize()
+        monkeypatch.setenv('VMP_FAST_2D', '0')
+        rt = rtol_for(dt, D)
+        ctx = dict(shape=list(shape), student=student, injected='noise' in kw)
+        check('2d engine r_nk', torch.exp(out['log_r']), torch.exp(ref['log_r']), rt, 1e-3, **ctx)
+        check('2d engine x_k', out['x_k_samples'], ref['x_k_samples'], rt, 1.0, **ctx)
+        agree = (out['z'] == ref['z']).double().mean().item()
+        assert agree >= 0.99, agree
+        m = out['z'] == ref['z']
+        check('2d engine x_sample', out['x_sample'][m], ref['x_sample'][m], rt, 1.0, **ctx)
+        scale = float(ref['elbo_acc'][:2].abs().max())
+        check('2d engine elbo', out['elbo_acc'][:3], ref['elbo_acc'][:3], rt, scale, **ctx)
+        assert float(out['elbo_acc'][3]) == 0.0
+
+
 @pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
 @pytest.mark.parametrize('case', ['gmm_sweep_a', 'gmm_sweep_b'])
 def test_gmm_sweep_vs_reference_golden(case, dt):

@@ -11,6 +11,7 @@
 // The categorical draw follows tf.multinomial's GPU kernel (multinomial_op_gpu.cu.cc): z = argmax_k(logit_k + G_k),
 // G_k = -log(-log(u_k)); u[N,K] may be injected for parity tests, otherwise Philox(seed, pair).
 #include "local_step_fast.cuh"
+#include "local_step_fast2d.cuh"
 #include "pair_math.cuh"
 
 #include <cstdlib>
@@ -212,6 +213,10 @@ static bool fast_enabled() {
     const char* e = std::getenv("VMP_FORCE_GENERIC");
     return !(e && e[0] == '1');
 }
+static bool engine2d_enabled() {
+    const char* e = std::getenv("VMP_FAST_2D");
+    return e && e[0] == '1';
+}
 static bool tma_enabled() {
     const char* e = std::getenv("VMP_NO_TMA");
     return !(e && e[0] == '1');
@@ -234,6 +239,13 @@ static int try_fast(int64_t N, int K, int D, int S, const float* eta1, const flo
     const int minb = D == 64 ? 1 : 2;
     if (smem * minb > 220 * 1024) return -100;
     float* recs = static_cast<float*>(work);
+    if (D == 64 && engine2d_enabled() && fast2d_smem_bytes(K) <= 220 * 1024 && tma_enabled()) {
+        // 2-D cyclic engine (local_step_fast2d.cuh); its record is smaller than the row-owned one, same workspace
+        launch_pack_fast2d_records(K, phi_rec, theta_rec, recs, st);
+        if (int e = launch_status()) return e;
+        FastParams p2{N, K, S, den_mode, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
+        return launch_fast2d_64(p2, st);
+    }
     launch_pack_fast_records(K, D, phi_rec, theta_rec, recs, st);
     if (int e = launch_status()) return e;
     FastParams p{N, K, S, den_mode, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
