@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
 
             // ---------------- phase 2: right-looking Cholesky with the two forward substitutions riding along
             float q = 0.f, hl2 = 0.f;                                     // hl2 = sum_j log2(pivot_j)
+            float yq[4], iq[4];
             static_for<0, D>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 constexpr int rj = j / BS, lj = j % BS;
@@ -311,7 +312,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 const float yj = __shfl_sync(FULL, g[rj] * inv, lj, BS);
                 const float y1j = __shfl_sync(FULL, g1[rj] * inv, lj, BS);
                 q = fmaf(yj, y1j, q);
-                if (gl == lj) { ab[j] = yj; ib[j] = inv; }               // kept in smem: frees 8 registers
+                // a_j and 1/L_jj go to shared memory (frees 8 registers); both are group-uniform, so four columns are
+                // batched into one 128-bit store each by lane 0 (6 fewer wavefronts per 4 columns than scalar stores)
+                yq[j & 3] = yj;
+                iq[j & 3] = inv;
+                if constexpr ((j & 3) == 3) {
+                    if (gl == 0) {
+                        *reinterpret_cast<float4*>(ab + j - 3) = make_float4(yq[0], yq[1], yq[2], yq[3]);
+                        *reinterpret_cast<float4*>(ib + j - 3) = make_float4(iq[0], iq[1], iq[2], iq[3]);
+                    }
+                }
                 float* cw = col + (j & 1) * D;
 #pragma unroll
                 for (int r = rj; r < ROWS; ++r) {
