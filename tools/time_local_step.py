@@ -34,11 +34,10 @@ def main():
     peak = 148 * 128 * 2 * 1.965e9
     ref = None
     for v in a.variants.split(','):
-        os.environ['VMP_FAST_VARIANT'] = v.replace('g', '').replace('2dp', '0').replace('2d', '0')
+        os.environ['VMP_FAST_VARIANT'] = v.replace('g', '').replace('2d', '0')
         os.environ['VMP_FORCE_GENERIC'] = '1' if v == 'g' else '0'
         os.environ['VMP_FAST_WIDE'] = '1' if v == 'w' else '0'
         os.environ['VMP_FAST_2D'] = '1' if v.startswith('2d') else '0'
-        os.environ['VMP_FAST_2D_PUB32'] = '1' if v == '2dp' else '0'
         os.environ['VMP_FAST_PF'] = v[2:] if v.startswith('pf') else '4'
         out = core.local_step(eta1, eta2d, phi_rec, theta_rec, a.S, seed=5, workspace=ws)   # warm-up
         torch.cuda.synchronize()

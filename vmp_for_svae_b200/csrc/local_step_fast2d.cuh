@@ -55,7 +55,7 @@ __device__ __forceinline__ void fmul2_bcast(float& d0, float& d1, float a0, floa
         : "f"(a0), "f"(a1), "f"(s));
 }
 
-template <int D, int WARPS, bool PUB32>
+template <int D, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) local_step_fast2d_kernel(const FastParams p) {
     using G = Fast2dGeom<D>;
     constexpr int NB = G::NB, RS = G::RS, MAT = G::MAT, REC = G::REC, GS = G::GS, PPC = WARPS * 2;
@@ -214,26 +214,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) local_step_fast2d_kernel(const 
                 constexpr int ja = j / 4, jr = j % 4, t0 = ja / 4;
                 float* cbw = cb + (j & 1) * 4 * RS;
                 if (pc == jr) {
-                    if constexpr (PUB32) {
-                        // scalar stores straight from the matrix registers (no repacking moves)
-                        if constexpr (ja % 2 == 1) cbw[pr * RS + ja - 1] = 0.f;      // partner of the first update pair
-                        cbw[pr * RS + ja] = (pr > jr) ? A[ja][ja] : 0.f;
+                    static_for<t0, NB / 4 + 1>([&](auto tc) {
+                        constexpr int t = decltype(tc)::value;
+                        float v[4];
 #pragma unroll
-                        for (int a = ja + 1; a <= NB; ++a) cbw[pr * RS + a] = A[a][ja];
-                    } else {
-                        static_for<t0, NB / 4 + 1>([&](auto tc) {
-                            constexpr int t = decltype(tc)::value;
-                            float v[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int a = 4 * t + i;
-                                if (a < ja || a > NB) v[i] = 0.f;
-                                else if (a == ja) v[i] = (pr > jr) ? A[ja][ja] : 0.f;
-                                else v[i] = A[a][ja];
-                            }
-                            *reinterpret_cast<float4*>(cbw + pr * RS + 4 * t) = make_float4(v[0], v[1], v[2], v[3]);
-                        });
-                    }
+                        for (int i = 0; i < 4; ++i) {
+                            const int a = 4 * t + i;
+                            if (a < ja || a > NB) v[i] = 0.f;
+                            else if (a == ja) v[i] = (pr > jr) ? A[ja][ja] : 0.f;
+                            else v[i] = A[a][ja];
+                        }
+                        *reinterpret_cast<float4*>(cbw + pr * RS + 4 * t) = make_float4(v[0], v[1], v[2], v[3]);
+                    });
                 }
                 const float piv = __shfl_sync(FULL, A[ja][ja], 5 * jr, 16);
                 float inv = rsqrt_approx(piv);
@@ -485,8 +477,7 @@ int launch_fast2d_64(const FastParams& p0, cudaStream_t st) {
     FastParams p = p0;
     p.ntiles = (p.N + PPC - 1) / PPC;
     const size_t smem = fast2d_smem_bytes(p.K);
-    const char* pe = std::getenv("VMP_FAST_2D_PUB32");
-    auto kern = (pe && pe[0] == '1') ? local_step_fast2d_kernel<64, WARPS, true> : local_step_fast2d_kernel<64, WARPS, false>;
+    auto kern = local_step_fast2d_kernel<64, WARPS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148, occ = 1;
