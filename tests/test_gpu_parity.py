@@ -406,3 +406,27 @@ def test_full_size_properties(shape):
     for t, t0, p, add in zip(theta, theta0, prior, [stats[:, 0], S2, stats[:, 2:2 + D], stats[:, 0], stats[:, 0] + 1]):
         want = 0.8 * t0.double() + 0.2 * (p.double() + add)
         assert float((t.double() - want).abs().max()) <= 2e-6 * float(want.abs().max())
+
+
+def test_chunked_host_step_equals_unchunked():
+    """svae_step_host with the chunked H2D/compute pipeline (what bench.py's e2e leg runs) == the one-shot step on
+    injected noise / Gumbel uniforms: same responsibilities, z, samples; statistics equal up to summation order."""
+    from vmp_for_svae_b200.step import SVAEStep, svae_step_host
+    N, K, D, S = 1000, 7, 16, 1
+    dt = torch.float32
+    prior, theta, phi_gmm, phi_enc, noise, u = _oracle_inputs(N, K, D, S, seed=21, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    host = tuple(t.to(dt).contiguous().pin_memory() for t in phi_enc)
+    nz, uu = noise.to(DEV, dt).contiguous(), u.to(DEV, dt).contiguous()
+    res = []
+    for chunk in (None, 256):
+        st = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False)
+        th = dev(theta)
+        elbo, alpha = svae_step_host(host, dev(phi_gmm), th, dev(prior), 0.3, st, chunk=chunk, noise=nz, u=uu)
+        torch.cuda.synchronize()
+        res.append((elbo, alpha, st.log_r.clone(), st.z.clone(), st.x_sample.clone(), [t.clone() for t in th]))
+    a, b = res
+    assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-9) and np.allclose(a[1], b[1], rtol=1e-6)
+    for x, y in zip(a[5], b[5]):
+        torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)

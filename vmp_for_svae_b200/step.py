@@ -65,17 +65,64 @@ class SVAEStep(object):
         return dict(log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc)
 
 
-def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, staging=None, chunk=None):
+def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, staging=None, chunk=None, noise=None,
+                   u=None):
     """End-to-end form of the step for HOST-resident encoder outputs (pinned CPU tensors): copies this rank's
-    eta1 / eta2_diag to the device, runs `stepper.step`, and reads the step's results (ELBO terms and the updated
-    theta's alpha) back to the host.  Returns (elbo_terms ndarray[4], alpha ndarray[K])."""
+    eta1 / eta2_diag to the device, runs the step, and reads the step's results (ELBO terms and the updated theta's
+    alpha) back to the host.  Returns (elbo_terms ndarray[4], alpha ndarray[K]).
+
+    chunk=None: one copy, then `stepper.step`.  chunk=C (points): the shard is processed in chunks of C points with the
+    host->device copy of chunk c+1 (own stream, two staging slots) overlapping the local step + statistics of chunk c;
+    the statistics and ELBO terms accumulate on the device and the all-reduce / natural-gradient update run once at
+    the end, so the result is the same VMP step.  The in-kernel noise stream is keyed per chunk (seed mixed with the
+    chunk index), i.e. a different but equally valid draw than the unchunked call; with injected `noise` / `u` the two
+    are identical (tests)."""
     eta1_h, eta2_h = phi_enc_host
-    if staging is None:
-        staging = (torch.empty(eta1_h.shape, dtype=eta1_h.dtype, device=stepper.device),
-                   torch.empty(eta2_h.shape, dtype=eta2_h.dtype, device=stepper.device))
-    staging[0].copy_(eta1_h, non_blocking=True)
-    staging[1].copy_(eta2_h, non_blocking=True)
-    out = stepper.step(staging, phi_gmm, theta, prior, rho, seed=seed)
+    N = eta1_h.shape[0]
+    st = stepper
+    if chunk is None or chunk >= N:
+        if staging is None:
+            staging = (torch.empty(eta1_h.shape, dtype=eta1_h.dtype, device=st.device),
+                       torch.empty(eta2_h.shape, dtype=eta2_h.dtype, device=st.device))
+        staging[0].copy_(eta1_h, non_blocking=True)
+        staging[1].copy_(eta2_h, non_blocking=True)
+        out = st.step(staging, phi_gmm, theta, prior, rho, seed=seed, noise=noise, u=u)
+    else:
+        chunk = int(chunk)
+        if getattr(st, '_chunk_state', None) is None or st._chunk_state[0] != chunk:
+            slots = [tuple(torch.empty(chunk, st.D, dtype=st.dtype, device=st.device) for _ in range(2)) for _ in range(2)]
+            st._chunk_state = (chunk, slots, torch.cuda.Stream(device=st.device),
+                               [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)])
+        _, slots, cstream, ready, free = st._chunk_state
+        cur = torch.cuda.current_stream(st.device)
+        core.phi_prepare(phi_gmm[0], phi_gmm[1], phi_gmm[2], out=st.phi_rec)
+        if st.den_mode == core.DEN_GAUSS:
+            core.theta_prepare_gauss(theta, out=st.theta_rec)
+        else:
+            core.theta_prepare_student(theta, out=st.theta_rec)
+        st.red.zero_()
+        for ev in free:
+            ev.record(cur)
+        nchunks = (N + chunk - 1) // chunk
+        for c in range(nchunks):
+            lo, hi = c * chunk, min(N, (c + 1) * chunk)
+            m, slot = hi - lo, c & 1
+            with torch.cuda.stream(cstream):
+                cstream.wait_event(free[slot])                       # the step of chunk c-2 is done with this slot
+                slots[slot][0][:m].copy_(eta1_h[lo:hi], non_blocking=True)
+                slots[slot][1][:m].copy_(eta2_h[lo:hi], non_blocking=True)
+                ready[slot].record(cstream)
+            cur.wait_event(ready[slot])
+            core.local_step(slots[slot][0][:m], slots[slot][1][:m], st.phi_rec, st.theta_rec, st.S, den_mode=st.den_mode,
+                            noise=None if noise is None else noise[lo:hi], u=None if u is None else u[lo:hi],
+                            seed=(int(seed) * 0x9E3779B97F4A7C15 + c) & 0xFFFFFFFFFFFFFFFF, log_r=st.log_r[lo:hi],
+                            x_sample=st.x_sample[lo:hi], z=st.z[lo:hi], elbo_acc=st.elbo_acc, workspace=st.workspace)
+            free[slot].record(cur)
+            core.suffstats(st.x_sample[lo:hi], st.log_r[lo:hi], r_is_log=True, stats=st.stats)
+        if st.use_dist:
+            torch.distributed.all_reduce(st.red, group=st.pg)
+        core.ng_update(st.stats, rho, prior, theta)
+        out = dict(elbo_acc=st.elbo_acc)
     elbo = out['elbo_acc'].to('cpu', non_blocking=False)
     alpha = theta[0].to('cpu')
     return elbo.numpy(), alpha.numpy()
