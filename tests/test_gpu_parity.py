@@ -430,3 +430,37 @@ def test_chunked_host_step_equals_unchunked():
     assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-9) and np.allclose(a[1], b[1], rtol=1e-6)
     for x, y in zip(a[5], b[5]):
         torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('N', [128, 1000, 33000])
+@pytest.mark.parametrize('r_is_log', [False, True])
+def test_tensor_core_suffstats_equals_fp32_kernel_and_fp64(N, r_is_log, monkeypatch):
+    """suffstats_tc.cu (tcgen05, split-tf32 operands, fp64 drains) for D = 64 against the FP32 kernel and an fp64 torch
+    contraction; tolerance (of each block's magnitude) 2e-6 for the FP32 kernel, 4e-6 for the tensor-core path (split-tf32
+    products are fp32-accurate, the tensor core's fp32 accumulation truncates within a 512-point run)."""
+    from vmp_for_svae_b200 import core
+    K, D = 6, 64
+    g = torch.Generator().manual_seed(N)
+    x = (torch.randn(N, D, generator=g, dtype=torch.float64) * 1.5 + 0.3).to(DEV, torch.float32)
+    logits = 3.0 * torch.randn(N, K, generator=g, dtype=torch.float64)
+    r64 = torch.softmax(logits, dim=1)
+    rin = (torch.log(r64) if r_is_log else r64).to(DEV, torch.float32).contiguous()
+    outs = {}
+    for mode in ('1', '0'):
+        monkeypatch.setenv('VMP_SUFFSTATS_TC', mode)
+        outs[mode] = core.suffstats(x, rin, r_is_log=r_is_log).cpu()
+    torch.cuda.synchronize()
+    monkeypatch.setenv('VMP_SUFFSTATS_TC', '1')
+    w = (torch.exp(rin.double()) if r_is_log else rin.double()).cpu()
+    xd = x.double().cpu()
+    ref = torch.zeros_like(outs['1'])
+    ref[:, 0] = w.sum(0); ref[:, 1] = w.sum(0)
+    ref[:, 2:2 + D] = w.t() @ xd
+    ref[:, 2 + D:] = torch.einsum('nk,ni,nj->kij', w, xd, xd).reshape(K, D * D)
+    for name, got in (('tensor-core', outs['1']), ('fp32', outs['0'])):
+        for lo, hi in ((0, 2), (2, 2 + D), (2 + D, 2 + D + D * D)):
+            scale = float(ref[:, lo:hi].abs().max())
+            err = float((got[:, lo:hi] - ref[:, lo:hi]).abs().max()) / scale
+            assert err < (4e-6 if name == 'tensor-core' else 2e-6), (name, N, (lo, hi), err)
+    S = outs['1'][:, 2 + D:].reshape(K, D, D)
+    assert torch.equal(S, S.transpose(1, 2))            # mirrored lower triangle: exactly symmetric

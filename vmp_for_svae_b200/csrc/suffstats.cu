@@ -10,6 +10,8 @@
 // atomicAdd per output per CTA.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace vmp {
 
 constexpr int SS_CH = 64;      // points per shared-memory chunk
@@ -292,6 +294,19 @@ static int launch_suffstats_small(int64_t N, int K, const T* x, const T* r, int 
     return launch_status();
 }
 
+// tensor-core contraction (suffstats_tc.cu): fp32, D = 64, even K, GMM weights; VMP_SUFFSTATS_TC=0 disables it
+int suffstats_tc(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, double* stats, cudaStream_t st);
+template <typename T>
+static int suffstats_tc_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, cudaStream_t) { return -100; }
+template <>
+int suffstats_tc_dispatch<float>(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
+                                 double* stats, cudaStream_t st) {
+    if (u_nk != nullptr) return -100;
+    const char* e = std::getenv("VMP_SUFFSTATS_TC");
+    if (e && e[0] == '0') return -100;
+    return suffstats_tc(N, K, D, x, r, r_is_log, stats, st);
+}
+
 template <typename T>
 int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
               void* stream) {
@@ -299,6 +314,7 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     if (N == 0) return VMP_OK;
     if (!x || !r || !stats) return VMP_E_BADARG;
+    if (int rc = suffstats_tc_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream); rc != -100) return rc;
 #define VMP_SSM(DD) \
     case DD: return launch_suffstats_small<T, DD>(N, K, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream)
     switch (D) {
