@@ -27,6 +27,7 @@ namespace vmp {
 __device__ int g_suffstats_tc_status = 0;      // set to 1 if an mbarrier wait ever ran out of its spin budget
 
 constexpr int TC_D = 64, TC_PC = 32, TC_THREADS = 256, TC_FLUSH = 16;
+constexpr int TC_ITEMS = (TC_D * TC_PC / 4) / TC_THREADS;      // (feature, point-quad) items per builder thread
 constexpr int TC_TILE = TC_D * TC_PC;                 // floats per operand tile (8 KB)
 constexpr int TC_RAWLD = TC_D + 4;                    // padded row of the staged x chunk
 constexpr int TC_DLD = TC_D + 1;                      // padded row of the fp64 accumulators
@@ -66,7 +67,7 @@ __device__ __forceinline__ float tc_hi(float v) {
 __device__ __forceinline__ void tc_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void tc_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// Threads 0..255 build operand tiles and drain accumulators; warp 8 only issues the MMAs (warp specialisation keeps the
+// Threads 0..TC_THREADS-1 build operand tiles and drain accumulators; the last warp only issues the MMAs (warp specialisation keeps the
 // single-thread issue sequence off the builders' critical path).  The two components of the CTA are stacked along M:
 // A = [(w_k0 . x)^T ; (w_k1 . x)^T] is 128 x 32 per chunk, so one M = 128 MMA serves both at the full tensor rate and
 // TMEM lane m holds row m % 64 of component k0 + m / 64.
@@ -159,7 +160,7 @@ suffstats_tc_kernel(int64_t N, int K, int64_t pts_per_slice, const float* __rest
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // this thread's items: feature j, point quads q0 and q0 + 4
+        // this thread's items: feature j, point quads q0 + (TC_THREADS / 64) * h
         const int j = tid & 63, q0 = tid >> 6;
         const int toff = (j >> 3) * 256 + (j & 7) * 4;      // + q * 32: float offset of (row j, points 4q..4q+3) in a 64-row tile
         float sx[2] = {0.f, 0.f}, sw[2] = {0.f, 0.f};
@@ -218,8 +219,8 @@ suffstats_tc_kernel(int64_t N, int K, int64_t pts_per_slice, const float* __rest
             float* tb = tiles + buf * 6 * TC_TILE;
             const float* rw = raw + buf * TC_PC * TC_RAWLD;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int q = q0 + 4 * h;
+            for (int h = 0; h < TC_ITEMS; ++h) {
+                const int q = q0 + (TC_THREADS / 64) * h;
                 float xv[4], hv[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
