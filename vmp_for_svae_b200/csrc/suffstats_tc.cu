@@ -46,7 +46,7 @@ __device__ __forceinline__ void tc_mma(uint32_t taddr, uint64_t da, uint64_t db,
 }
 // returns false if the phase did not complete within the spin budget (a broken descriptor must not hang the GPU)
 __device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity) {
-    for (int spin = 0; spin < (1 << 28); ++spin) {
+    for (int spin = 0; spin < (1 << 22); ++spin) {       // each try_wait blocks for a bounded time itself
         uint32_t done;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done)
