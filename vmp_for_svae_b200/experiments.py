@@ -65,8 +65,11 @@ def perturb_data(x, noise_ratio=0.1, noise_mean=0.0, noise_stddev=10.0, seed=0):
     return x
 
 
-def make_dataset(dataset, ratio_tr=0.7, seed_split=0, noise_level=0.1):
-    """data.py:9-128 for the array datasets -> (X_tr, lbl_tr, X_te, lbl_te) numpy; labels are class indices."""
+def make_dataset(dataset, ratio_tr=0.7, seed_split=0, noise_level=0.1, path_datadir='../datasets'):
+    """data.py:9-128 for the array datasets -> (X_tr, lbl_tr, X_te, lbl_te) numpy; labels are class indices.
+    'pinwheel' / 'noisy-pinwheel' are generated; 'auto', 'geyser', 'aggregation' read the reference's files from
+    `path_datadir` when present (they are not shipped); 'auto-like' is a synthetic 6-D stand-in for 'auto'."""
+    import os
     if dataset in ('pinwheel', 'noisy-pinwheel'):
         data, labels = make_pinwheel_data(0.3, 0.05, 5, 200, 0.25)
     elif dataset == 'auto-like':
@@ -74,6 +77,25 @@ def make_dataset(dataset, ratio_tr=0.7, seed_split=0, noise_level=0.1):
         labels = rs.randint(0, 5, 392)
         centres, mix = 2.0 * rs.randn(5, 6), rs.randn(5, 6, 6) * 0.4
         data = centres[labels] + np.einsum('nij,nj->ni', mix[labels], rs.randn(392, 6))
+    elif dataset in ('auto', 'geyser', 'aggregation'):
+        import pandas as pd
+        path = {'auto': 'Auto/auto-mpg.csv', 'geyser': 'geyser', 'aggregation': 'Aggregation.txt'}[dataset]
+        path = os.path.join(path_datadir, path)
+        if not os.path.exists(path):
+            raise FileNotFoundError("dataset '%s' needs %s (not shipped with this repository); use 'auto-like' or "
+                                    "'pinwheel' for a self-contained run" % (dataset, path))
+        if dataset == 'auto':                                         # data.py:56-75
+            raw = pd.read_csv(path, sep=',', header=None).values
+            raw = raw[raw[:, 3] != '?']
+            cyl = raw[:, 1].astype(np.int64)
+            labels = np.select([cyl == 3, cyl == 4, cyl == 5, cyl == 6, cyl == 8], [0, 1, 2, 3, 4])
+            data = raw[:, [0, 2, 3, 4, 5, 6]].astype(np.float64)
+        elif dataset == 'geyser':                                     # data.py:41-44
+            data = pd.read_csv(path, sep=' ', header=None).values[:, [1, 2]].astype(np.float64)
+            labels = (data[:, 1] > 20).astype(np.int64)
+        else:                                                         # data.py:50-54
+            raw = pd.read_csv(path, sep='\t', header=None).values
+            data, labels = raw[:, 0:2].astype(np.float64), raw[:, 2].astype(np.int64) - 1
     else:
         raise Exception("Dataset '%s' does not exist." % dataset)
     rs = np.random.RandomState(seed_split)
@@ -83,9 +105,12 @@ def make_dataset(dataset, ratio_tr=0.7, seed_split=0, noise_level=0.1):
     X_tr, X_te = data[tr], data[te]
     if dataset == 'noisy-pinwheel':
         X_tr = perturb_data(X_tr, noise_ratio=noise_level, seed=seed_split)
-    if dataset == 'auto-like':                                        # data.py:114-117 : standardise, times 5
+    if dataset in ('auto-like', 'auto'):                              # data.py:114-117 : standardise, times 5
         mu, sd = X_tr.mean(0), X_tr.std(0)
         X_tr, X_te = (X_tr - mu) / sd * 5.0, (X_te - mu) / sd * 5.0
+    elif dataset not in ('pinwheel', 'noisy-pinwheel'):               # data.py:118-121
+        mu, sd = X_tr.mean(0), X_tr.std(0)
+        X_tr, X_te = (X_tr - mu) / sd, (X_te - mu) / sd
     return X_tr, labels[tr], X_te, labels[te]
 
 
