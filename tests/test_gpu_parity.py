@@ -155,7 +155,7 @@ def _oracle_inputs(N, K, D, S, seed, spread):
 
 STEP_SHAPES = [(100, 10, 2, 10), (274, 10, 6, 10), (257, 32, 8, 2), (96, 7, 16, 1), (64, 12, 32, 1), (40, 9, 64, 1),
                (33, 5, 11, 3), (1, 3, 4, 1), (130, 1, 5, 2), (67, 5, 16, 3), (50, 3, 32, 2), (19, 4, 64, 2),
-               (300, 20, 24, 1)]
+               (300, 20, 24, 1), (300, 6, 64, 1), (200, 5, 64, 1)]
 
 
 @pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
