@@ -106,7 +106,8 @@ size_t vmp_svae_local_step_workspace_bytes(int K, int D);
  * (svae.py:199-322); theta is a constant there (tf.stop_gradient, svae.py:211-214).  Computes the gradients of
  *      sum(gx * x_k_samples) + sum(glr * log_r) + greg * regulariser          (regulariser == elbo_acc[2] of the step)
  * w.r.t. eta1[N,D], eta2_diag[N,D] and the raw phi_gmm (eta1_phi2[K,D], L_raw[K,D,D], pi_raw[K]).  The caller passes
- * the same noise/seed and the log_r of the forward call; gx[N,K,S,D], glr[N,K] are the upstream gradients.
+ * the same noise/seed and the log_r of the forward call; gx[N,K,S,D], glr[N,K] are the upstream gradients; greg_dev
+ * (device scalar, may be NULL) overrides greg so that no host synchronisation is needed (CUDA-graph capture).
  * theta_rec_bar[K, vmp_theta_record_len(D)] (may be NULL) receives the gradient w.r.t. the theta record (W lower | m |
  * cden, zeros): compute_elbo_smm trains mu_k, L_k of the Student-t components by gradient (svae.py:265-322 has no
  * stop_gradient on them; experiments.py:154-174).  D <= VMP_BWD_MAX_D, K <= 256.  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
@@ -115,14 +116,15 @@ size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D);
 int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                                 const float* eta1_phi2, const float* L_raw, const float* pi_raw, const float* phi_rec,
                                 const float* theta_rec, int den_mode, const float* noise, uint64_t seed,
-                                const float* log_r, const float* gx, const float* glr, double greg, float* eta1_bar,
+                                const float* log_r, const float* gx, const float* glr, double greg, const float* greg_dev,
+                                float* eta1_bar,
                                 float* eta2_diag_bar, float* eta1_phi2_bar, float* L_raw_bar, float* pi_raw_bar,
                                 float* theta_rec_bar, void* workspace, size_t workspace_bytes, void* stream);
 int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
                                 const double* eta1_phi2, const double* L_raw, const double* pi_raw,
                                 const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
                                 uint64_t seed, const double* log_r, const double* gx, const double* glr, double greg,
-                                double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
+                                const double* greg_dev, double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
                                 double* pi_raw_bar, double* theta_rec_bar, void* workspace, size_t workspace_bytes,
                                 void* stream);
 
@@ -146,12 +148,13 @@ int vmp_suffstats_f64(int64_t N, int K, int D, const double* x, const double* r,
  * Replaces svae.m_step (svae.py:154-176) + svae.update_gmm_params (376-403):
  * theta* = prior + [N_k, sum r x x^T, sum r x, N_k, N_k + 1]; theta <- (1-rho) theta + rho theta*, in place.
  * theta_star_* (optional, may be NULL) receive theta*.  With only_alpha != 0 only alpha is touched
- * (svae.m_step_smm, svae.py:179-196).                                                                 */
-int vmp_ng_update_f32(int K, int D, const double* stats, double rho, int only_alpha,
+ * (svae.m_step_smm, svae.py:179-196).  rho_dev (device pointer, may be NULL) overrides rho: a device-resident
+ * step size lets a captured CUDA graph follow the decaying CVI schedule (experiments.py:143-147).          */
+int vmp_ng_update_f32(int K, int D, const double* stats, double rho, const double* rho_dev, int only_alpha,
                       const float* p_alpha, const float* p_A, const float* p_b, const float* p_beta, const float* p_vhat,
                       float* alpha, float* A, float* b, float* beta, float* v_hat,
                       float* s_alpha, float* s_A, float* s_b, float* s_beta, float* s_vhat, void* stream);
-int vmp_ng_update_f64(int K, int D, const double* stats, double rho, int only_alpha,
+int vmp_ng_update_f64(int K, int D, const double* stats, double rho, const double* rho_dev, int only_alpha,
                       const double* p_alpha, const double* p_A, const double* p_b, const double* p_beta, const double* p_vhat,
                       double* alpha, double* A, double* b, double* beta, double* v_hat,
                       double* s_alpha, double* s_A, double* s_b, double* s_beta, double* s_vhat, void* stream);

@@ -21,11 +21,11 @@ _SIGS_T = {
     'vmp_svae_local_step': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_u64, c_ptr,
                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr],
     'vmp_svae_local_step_bwd': [c_i64, c_int, c_int, c_int] + [c_ptr] * 7 + [c_int, c_ptr, c_u64, c_ptr, c_ptr, c_ptr,
-                                                                               c_dbl] + [c_ptr] * 6 +
+                                                                               c_dbl, c_ptr] + [c_ptr] * 6 +
                                [c_ptr, ctypes.c_size_t, c_ptr],
     'vmp_fill_noise': [c_i64, c_int, c_int, c_int, c_u64, c_ptr, c_ptr, c_ptr],
     'vmp_suffstats': [c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr],
-    'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_int] + [c_ptr] * 15 + [c_ptr],
+    'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_ptr, c_int] + [c_ptr] * 15 + [c_ptr],
     'vmp_mixture_mstep': [c_int, c_int, c_int, c_ptr] + [c_ptr] * 12 + [c_ptr],
     'vmp_mixture_estep': [c_i64, c_int, c_int] + [c_ptr] * 12 + [c_ptr],
     'vmp_spd_inverse': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],

@@ -39,7 +39,7 @@ class _LocalStepFn(torch.autograd.Function):
         K = phi_rec.shape[0]
         gx = torch.zeros(N, K, ctx.S, D, dtype=eta1.dtype, device=eta1.device) if gx is None else gx.contiguous()
         glr = torch.zeros(N, K, dtype=eta1.dtype, device=eta1.device) if glr is None else glr.contiguous()
-        greg = 0.0 if greg is None else float(greg)     # one scalar sync; the loss weight is 1 or -1 in practice
+        greg = 0.0 if greg is None else greg            # stays on the device: no host synchronisation
         want_th = ctx.needs_input_grad[5]
         g = core.local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, ctx.S, log_r, gx,
                                      glr, greg, den_mode=ctx.den_mode, noise=ctx.noise, seed=ctx.seed,

@@ -116,6 +116,10 @@ def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, thet
     log_r = _chk(log_r, (N, K), dt, 'log_r'); gx = _chk(gx, (N, K, S, D), dt, 'gx'); glr = _chk(glr, (N, K), dt, 'glr')
     if noise is not None:
         noise = _chk(noise, (N, K, D, S), dt, 'noise')
+    greg_dev = None
+    if isinstance(greg, torch.Tensor):          # device scalar: no host synchronisation (CUDA-graph friendly)
+        greg_dev = greg.detach().reshape(1).to(device=dev, dtype=dt).contiguous()
+        greg = 0.0
     lib = _lib.load()
     nbytes = int(lib.vmp_svae_local_step_bwd_workspace_bytes(K, D))
     work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
@@ -123,7 +127,7 @@ def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, thet
     th_bar = torch.empty_like(theta_rec) if want_theta_rec_bar else None
     _lib.call('vmp_svae_local_step_bwd', dt, N, K, D, S, ptr(eta1), ptr(eta2_diag), ptr(eta1_phi2), ptr(L_raw),
               ptr(pi_raw), ptr(phi_rec), ptr(theta_rec), int(den_mode), ptr(noise), int(seed) & 0xFFFFFFFFFFFFFFFF,
-              ptr(log_r), ptr(gx), ptr(glr), float(greg), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
+              ptr(log_r), ptr(gx), ptr(glr), float(greg), ptr(greg_dev), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
               ptr(out[4]), ptr(th_bar), ptr(work), nbytes, stream_ptr(dev))
     return tuple(out) + ((th_bar,) if want_theta_rec_bar else ())
 
@@ -152,14 +156,19 @@ def suffstats(x, r, r_is_log=False, u_nk=None, stats=None):
 
 
 def ng_update(stats, rho, prior, theta, only_alpha=False, want_star=False):
-    """theta <- (1-rho) theta + rho (prior + stats terms), in place.  Returns theta* when want_star."""
+    """theta <- (1-rho) theta + rho (prior + stats terms), in place.  Returns theta* when want_star.
+    rho: python float, or a 1-element float64 CUDA tensor (device-resident step size, CUDA-graph friendly)."""
+    rho_dev = None
+    if isinstance(rho, torch.Tensor):
+        rho_dev = _chk(rho.reshape(1), (1,), torch.float64, 'rho')
+        rho = 0.0
     alpha = theta[0]
     K = alpha.shape[0]
     dt, dev = alpha.dtype, alpha.device
     if only_alpha:
         D = (stats.shape[1] and int(round((-1 + (1 + 4 * (stats.shape[1] - 2)) ** 0.5) / 2)))
         star = [torch.empty_like(alpha)] if want_star else [None]
-        _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), 1, ptr(prior[0].contiguous()), None, None, None,
+        _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), ptr(rho_dev), 1, ptr(prior[0].contiguous()), None, None, None,
                   None, ptr(alpha), None, None, None, None, ptr(star[0]), None, None, None, None, stream_ptr(dev))
         return star if want_star else None
     D = theta[2].shape[1]
@@ -167,7 +176,7 @@ def ng_update(stats, rho, prior, theta, only_alpha=False, want_star=False):
         assert t.is_contiguous() and t.dtype == dt
     p = [t.contiguous() for t in prior]
     star = [torch.empty_like(t) for t in theta] if want_star else [None] * 5
-    _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), 0, ptr(p[0]), ptr(p[1]), ptr(p[2]), ptr(p[3]), ptr(p[4]),
+    _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), ptr(rho_dev), 0, ptr(p[0]), ptr(p[1]), ptr(p[2]), ptr(p[3]), ptr(p[4]),
               ptr(theta[0]), ptr(theta[1]), ptr(theta[2]), ptr(theta[3]), ptr(theta[4]),
               ptr(star[0]), ptr(star[1]), ptr(star[2]), ptr(star[3]), ptr(star[4]), stream_ptr(dev))
     return star if want_star else None

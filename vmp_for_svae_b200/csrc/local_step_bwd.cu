@@ -24,10 +24,11 @@ template <typename T, int DT, bool TH>
 __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, int Drt, int S, int PTS, int den_mode, const T* __restrict__ eta1,
                       const T* __restrict__ eta2d, const T* __restrict__ phi_rec, const T* __restrict__ theta_rec,
                       const T* __restrict__ noise, uint64_t seed, const T* __restrict__ log_r,
-                      const T* __restrict__ gx, const T* __restrict__ glr, T greg,
+                      const T* __restrict__ gx, const T* __restrict__ glr, T greg_host, const T* __restrict__ greg_dev,
                       T* __restrict__ eta1_bar, T* __restrict__ eta2d_bar, double* __restrict__ kacc) {
     constexpr int DM = DT ? DT : BWD_MAX_D;
     const int D = DT ? DT : Drt;
+    const T greg = greg_dev != nullptr ? *greg_dev : greg_host;
     extern __shared__ __align__(8) unsigned char smraw[];
     double* pacc = reinterpret_cast<double*>(smraw);                 // [PTS][2*D]  eta1_bar | p1_bar per point
     T* gsum = reinterpret_cast<T*>(pacc + (size_t)PTS * 2 * D);      // [PTS]       sum_k glr'
@@ -395,15 +396,15 @@ local_step_bwd_epilogue_kernel(int K, int D, const T* __restrict__ eta1_phi2, co
 template <typename T, int DT, bool TH>
 static cudaError_t launch_bwd_main(int64_t N, int K, int D, int S, int den_mode, const T* eta1, const T* eta2d,
                                    const T* phi_rec, const T* theta_rec, const T* noise, uint64_t seed, const T* log_r,
-                                   const T* gx, const T* glr, T greg, T* eta1_bar, T* eta2d_bar, double* kacc,
-                                   cudaStream_t st) {
+                                   const T* gx, const T* glr, T greg, const T* greg_dev, T* eta1_bar, T* eta2d_bar,
+                                   double* kacc, cudaStream_t st) {
     const int PTS = K >= 128 ? 1 : 128 / K;
     const int threads = ((PTS * K + 31) / 32) * 32;
     const size_t smem = (size_t)PTS * 2 * D * sizeof(double) + (size_t)PTS * sizeof(T);
     const int64_t grid = (N + PTS - 1) / PTS;
     local_step_bwd_kernel<T, DT, TH><<<(unsigned)grid, threads, smem, st>>>(N, K, D, S, PTS, den_mode, eta1, eta2d, phi_rec,
                                                                         theta_rec, noise, seed, log_r, gx, glr, greg,
-                                                                        eta1_bar, eta2d_bar, kacc);
+                                                                        greg_dev, eta1_bar, eta2d_bar, kacc);
     return cudaGetLastError();
 }
 
@@ -411,7 +412,7 @@ template <typename T>
 static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* eta1_phi2,
                                const T* L_raw, const T* pi_raw, const T* phi_rec, const T* theta_rec, int den_mode,
                                const T* noise, uint64_t seed, const T* log_r, const T* gx, const T* glr, double greg,
-                               T* eta1_bar, T* eta2d_bar, T* h2_bar, T* L_raw_bar, T* pi_raw_bar,
+                               const T* greg_dev, T* eta1_bar, T* eta2d_bar, T* h2_bar, T* L_raw_bar, T* pi_raw_bar,
                                T* theta_rec_bar, void* work, size_t work_bytes, cudaStream_t st) {
     if (N < 0 || K < 1 || K > 256 || S < 1) return VMP_E_BADARG;
     if (D < 1 || D > BWD_MAX_D) return VMP_E_BADDIM;
@@ -428,19 +429,19 @@ static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, co
 #define VMP_BWD_CASE(DD)                                                                                              \
     case DD:                                                                                                          \
         e = theta_rec_bar ? launch_bwd_main<T, DD, true>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,   \
-                                                         seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc, st)  \
+                                                         seed, log_r, gx, glr, (T)greg, greg_dev, eta1_bar, eta2d_bar, kacc, st)  \
                           : launch_bwd_main<T, DD, false>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,  \
-                                                          seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc, st); \
+                                                          seed, log_r, gx, glr, (T)greg, greg_dev, eta1_bar, eta2d_bar, kacc, st); \
         break;
         switch (D) {
             VMP_BWD_CASE(1) VMP_BWD_CASE(2) VMP_BWD_CASE(3) VMP_BWD_CASE(4) VMP_BWD_CASE(5) VMP_BWD_CASE(6)
             VMP_BWD_CASE(7) VMP_BWD_CASE(8)
             default:
                 e = theta_rec_bar ? launch_bwd_main<T, 0, true>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,
-                                                                seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc, st)
+                                                                seed, log_r, gx, glr, (T)greg, greg_dev, eta1_bar, eta2d_bar, kacc, st)
                                   : launch_bwd_main<T, 0, false>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,
-                                                                 seed, log_r, gx, glr, (T)greg, eta1_bar, eta2d_bar, kacc,
-                                                                 st);
+                                                                 seed, log_r, gx, glr, (T)greg, greg_dev, eta1_bar, eta2d_bar,
+                                                                 kacc, st);
         }
 #undef VMP_BWD_CASE
         if (e != cudaSuccess) return (int)e;
@@ -460,11 +461,12 @@ size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D) {
 int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                                 const float* eta1_phi2, const float* L_raw, const float* pi_raw, const float* phi_rec,
                                 const float* theta_rec, int den_mode, const float* noise, uint64_t seed,
-                                const float* log_r, const float* gx, const float* glr, double greg, float* eta1_bar,
+                                const float* log_r, const float* gx, const float* glr, double greg, const float* greg_dev,
+                                float* eta1_bar,
                                 float* eta2_diag_bar, float* eta1_phi2_bar, float* L_raw_bar, float* pi_raw_bar,
                                 float* theta_rec_bar, void* workspace, size_t workspace_bytes, void* stream) {
     return vmp::svae_local_step_bwd<float>(N, K, D, S, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec,
-                                           den_mode, noise, seed, log_r, gx, glr, greg, eta1_bar, eta2_diag_bar,
+                                           den_mode, noise, seed, log_r, gx, glr, greg, greg_dev, eta1_bar, eta2_diag_bar,
                                            eta1_phi2_bar, L_raw_bar, pi_raw_bar, theta_rec_bar, workspace, workspace_bytes,
                                            static_cast<cudaStream_t>(stream));
 }
@@ -472,10 +474,10 @@ int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* et
                                 const double* eta1_phi2, const double* L_raw, const double* pi_raw,
                                 const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
                                 uint64_t seed, const double* log_r, const double* gx, const double* glr, double greg,
-                                double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
+                                const double* greg_dev, double* eta1_bar, double* eta2_diag_bar, double* eta1_phi2_bar, double* L_raw_bar,
                                 double* pi_raw_bar, double* theta_rec_bar, void* workspace, size_t workspace_bytes, void* stream) {
     return vmp::svae_local_step_bwd<double>(N, K, D, S, eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec,
-                                            den_mode, noise, seed, log_r, gx, glr, greg, eta1_bar, eta2_diag_bar,
+                                            den_mode, noise, seed, log_r, gx, glr, greg, greg_dev, eta1_bar, eta2_diag_bar,
                                             eta1_phi2_bar, L_raw_bar, pi_raw_bar, theta_rec_bar, workspace, workspace_bytes,
                                             static_cast<cudaStream_t>(stream));
 }

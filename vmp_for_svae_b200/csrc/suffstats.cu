@@ -353,11 +353,13 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
 // theta* = prior + [N_k, sum r x x^T, sum r x, N_k, N_k + 1]   (svae.m_step in natural parameters)
 // theta <- (1 - rho) theta + rho theta*                         (svae.update_gmm_params)
 template <typename T>
-__global__ void ng_update_kernel(int K, int D, const double* __restrict__ stats, double rho, int only_alpha,
+__global__ void ng_update_kernel(int K, int D, const double* __restrict__ stats, double rho_host,
+                                 const double* __restrict__ rho_dev, int only_alpha,
                                  const T* __restrict__ p_alpha, const T* __restrict__ p_A, const T* __restrict__ p_b,
                                  const T* __restrict__ p_beta, const T* __restrict__ p_vhat, T* alpha, T* A, T* b,
                                  T* beta, T* v_hat, T* s_alpha, T* s_A, T* s_b, T* s_beta, T* s_vhat) {
     const int k = blockIdx.x;
+    const double rho = rho_dev != nullptr ? *rho_dev : rho_host;     // device-resident step size: CUDA-graph replays
     const double* st = stats + (size_t)k * stats_len(D);
     const double Nk = st[0];
     if (threadIdx.x == 0) {
@@ -388,13 +390,13 @@ __global__ void ng_update_kernel(int K, int D, const double* __restrict__ stats,
 }
 
 template <typename T>
-int ng_update(int K, int D, const double* stats, double rho, int only_alpha, const T* p_alpha, const T* p_A,
+int ng_update(int K, int D, const double* stats, double rho, const double* rho_dev, int only_alpha, const T* p_alpha, const T* p_A,
               const T* p_b, const T* p_beta, const T* p_vhat, T* alpha, T* A, T* b, T* beta, T* v_hat, T* s_alpha,
               T* s_A, T* s_b, T* s_beta, T* s_vhat, void* stream) {
     if (K <= 0 || !stats || !p_alpha || !alpha) return VMP_E_BADARG;
     if (!only_alpha && (!p_A || !p_b || !p_beta || !p_vhat || !A || !b || !beta || !v_hat)) return VMP_E_BADARG;
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
-    ng_update_kernel<T><<<K, 256, 0, (cudaStream_t)stream>>>(K, D, stats, rho, only_alpha, p_alpha, p_A, p_b, p_beta,
+    ng_update_kernel<T><<<K, 256, 0, (cudaStream_t)stream>>>(K, D, stats, rho, rho_dev, only_alpha, p_alpha, p_A, p_b, p_beta,
                                                              p_vhat, alpha, A, b, beta, v_hat, s_alpha, s_A, s_b,
                                                              s_beta, s_vhat);
     return launch_status();
@@ -462,18 +464,20 @@ int vmp_suffstats_f64(int64_t N, int K, int D, const double* x, const double* r,
                       double* stats, void* stream) {
     return vmp::suffstats<double>(N, K, D, x, r, r_is_log, u_nk, stats, stream);
 }
-int vmp_ng_update_f32(int K, int D, const double* stats, double rho, int only_alpha, const float* p_alpha,
+int vmp_ng_update_f32(int K, int D, const double* stats, double rho, const double* rho_dev, int only_alpha,
+                      const float* p_alpha,
                       const float* p_A, const float* p_b, const float* p_beta, const float* p_vhat, float* alpha,
                       float* A, float* b, float* beta, float* v_hat, float* s_alpha, float* s_A, float* s_b,
                       float* s_beta, float* s_vhat, void* stream) {
-    return vmp::ng_update<float>(K, D, stats, rho, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta,
+    return vmp::ng_update<float>(K, D, stats, rho, rho_dev, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta,
                                  v_hat, s_alpha, s_A, s_b, s_beta, s_vhat, stream);
 }
-int vmp_ng_update_f64(int K, int D, const double* stats, double rho, int only_alpha, const double* p_alpha,
+int vmp_ng_update_f64(int K, int D, const double* stats, double rho, const double* rho_dev, int only_alpha,
+                      const double* p_alpha,
                       const double* p_A, const double* p_b, const double* p_beta, const double* p_vhat, double* alpha,
                       double* A, double* b, double* beta, double* v_hat, double* s_alpha, double* s_A, double* s_b,
                       double* s_beta, double* s_vhat, void* stream) {
-    return vmp::ng_update<double>(K, D, stats, rho, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta,
+    return vmp::ng_update<double>(K, D, stats, rho, rho_dev, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta,
                                   v_hat, s_alpha, s_A, s_b, s_beta, s_vhat, stream);
 }
 int vmp_mixture_mstep_f32(int K, int D, int is_smm, const double* stats, const float* alpha_0, const float* beta_0,

@@ -254,8 +254,72 @@ class SVAETrainer(object):
         return float(mse), float(ll)
 
 
+class GraphedSVAETrainer(SVAETrainer):
+    """The whole training iteration (minibatch gather, encoder, fused local step, decoder, both reverse kernels, Adam,
+    statistics, CVI update with the decaying step size) captured ONCE in a CUDA graph and replayed: the reference's
+    shapes (64-100 points, K = 10) are launch-bound, ~40 small launches per iteration.  Everything an iteration needs
+    is device-resident: minibatch indices, noise and Gumbel uniforms come from torch's graph-safe generator, the CVI
+    step size is a device scalar multiplied by decay^(1/1000) each replay, the upstream scalar of the regulariser
+    reaches the reverse kernel as a device pointer.  GMM variant ('svae-cvi')."""
+
+    def __init__(self, config, y_train, size_minibatch, device='cuda', nb_samples=10, stddev_init_nn=0.01,
+                 decoder_type='standard'):
+        super().__init__(config, y_train.shape[1], device=device, nb_samples=nb_samples, stddev_init_nn=stddev_init_nn,
+                         decoder_type=decoder_type)
+        assert not self.smm, 'graphed trainer: GMM variant only'
+        self.y_train, self.M = y_train, int(size_minibatch)
+        params = list(self.encoder.parameters()) + list(self.decoder.parameters()) + self.phi_gmm
+        self.opt = torch.optim.Adam(params, lr=config['lr'], eps=1e-8, capturable=True)
+        self.rho = torch.full((1,), float(config['lrcvi']), dtype=torch.float64, device=self.dev)
+        self.decay = float(config.get('decay_rate', 1.0)) ** (1.0 / 1000.0)
+        self.out = None
+        self.graph = None
+
+    def _iteration(self):
+        N, K, L, S = self.M, self.K, self.L, self.S
+        idx = torch.randint(0, self.y_train.shape[0], (N,), device=self.dev)
+        y = self.y_train[idx]
+        noise = torch.randn(N, K, L, S, device=self.dev)
+        u = torch.rand(N, K, device=self.dev)
+        eta1, eta2d = self.encoder(y)
+        x_k, log_r, reg, acc, x_samp, z = local_step_autograd(
+            eta1, eta2d, self.phi_gmm[0], self.phi_gmm[1], self.phi_gmm[2], core.theta_prepare_gauss(self.theta), S,
+            noise=noise, u=u, full=True)
+        neg_rec = decoder_loglike_autograd(y, self.decoder(x_k), torch.exp(log_r), self.decoder_type)
+        elbo = neg_rec - reg
+        (-elbo).backward()
+        stats = core.suffstats(x_samp, log_r.detach(), r_is_log=True)
+        core.ng_update(stats, self.rho, self.prior, self.theta)
+        self.opt.step()
+        self.rho.mul_(self.decay)                                       # experiments.py:143-147
+        return torch.stack([elbo.detach(), neg_rec.detach(), reg.detach(), acc[3].to(elbo.dtype)])
+
+    def capture(self, warmup=3):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.opt.zero_grad(set_to_none=True)
+                self._iteration()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self.global_step += warmup
+        self.graph = torch.cuda.CUDAGraph()
+        self.opt.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.out = self._iteration()                                # recorded, not executed
+        return self
+
+    def train_step(self, y=None):
+        """One replay = one training iteration on a fresh on-device minibatch.  -> tensor [elbo, neg_rec, reg, bad]."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        self.global_step += 1
+        return self.out
+
+
 def run_experiment(config, nb_iters=2000, size_minibatch=64, measurement_freq=500, device='cuda', verbose=True,
-                   nb_samples=10, nb_samples_te=100):
+                   nb_samples=10, nb_samples_te=100, graphed=False):
     """experiments.py:101-478 without TF session plumbing, plots and checkpoints.  -> (trainer, history list)."""
     torch.manual_seed(config.get('seed', 0))
     X_tr, l_tr, X_te, l_te = make_dataset(config['dataset'], noise_level=config.get('noise_level', 0.1))
@@ -263,16 +327,25 @@ def run_experiment(config, nb_iters=2000, size_minibatch=64, measurement_freq=50
     y_tr = torch.as_tensor(X_tr, dtype=torch.float32, device=dev)
     y_te = torch.as_tensor(X_te, dtype=torch.float32, device=dev)
     lbl_te = torch.as_tensor(l_te, device=dev)
-    tr = SVAETrainer(config, y_tr.shape[1], device=dev, nb_samples=nb_samples)
+    graphed = graphed and 'smm' not in config['method']
+    if graphed:
+        tr = GraphedSVAETrainer(config, y_tr, size_minibatch, device=dev, nb_samples=nb_samples).capture()
+    else:
+        tr = SVAETrainer(config, y_tr.shape[1], device=dev, nb_samples=nb_samples)
     g = torch.Generator(device='cpu').manual_seed(config.get('seed', 0))
     hist, t0 = [], time.time()
     for i in range(nb_iters):
-        idx = torch.randint(0, y_tr.shape[0], (size_minibatch,), generator=g).to(dev)   # shuffle_batch stand-in
-        out = tr.train_step(y_tr[idx].contiguous())
+        if graphed:
+            o = tr.train_step()
+            out = dict(elbo=o[0], neg_rec=o[1], reg=o[2], bad_pivots=o[3])
+        else:
+            idx = torch.randint(0, y_tr.shape[0], (size_minibatch,), generator=g).to(dev)   # shuffle_batch stand-in
+            out = tr.train_step(y_tr[idx].contiguous())
         if i % measurement_freq == 0 or i == nb_iters - 1 or i == 1:
             ev = tr.evaluate(y_te, lbl_te, nb_samples=nb_samples_te)
             ev.update(iter=i, neg_elbo_normed=-float(out['elbo']) / size_minibatch, sec=time.time() - t0,
-                      neg_rec=float(out['neg_rec']), reg=float(out['reg']), lrcvi=tr.lrcvi(),
+                      neg_rec=float(out['neg_rec']), reg=float(out['reg']),
+                      lrcvi=float(tr.rho) if graphed else tr.lrcvi(),
                       bad_pivots=float(out['bad_pivots']))
             if i == nb_iters - 1:
                 ev['imp_mse'], ev['imp_logprob'] = tr.imputation(y_te, nb_samples=nb_samples_te)
@@ -291,12 +364,13 @@ if __name__ == '__main__':
     ap.add_argument('--method', default='svae-cvi')
     ap.add_argument('--iters', type=int, default=2000)
     ap.add_argument('--out', default=None)
+    ap.add_argument('--graphed', action='store_true', help='replay the iteration from a CUDA graph (GMM variant)')
     a = ap.parse_args()
     pin = a.dataset != 'auto-like'
     cfg = create_schedule({'dataset': a.dataset, 'method': a.method, 'lr': [0.01 if pin else 0.0003],
                            'lrcvi': [0.1 if pin else 0.2], 'decay_rate': [1.0 if pin else 0.95], 'K': 10,
                            'L': [2 if pin else 6], 'U': 50 if 'smm' not in a.method else 40, 'DoF': 5, 'seed': 0})[0]
-    _, hist = run_experiment(cfg, nb_iters=a.iters, size_minibatch=100 if pin else 64)
+    _, hist = run_experiment(cfg, nb_iters=a.iters, size_minibatch=100 if pin else 64, graphed=a.graphed)
     if a.out:
         with open(a.out, 'w') as f:
             json.dump(dict(config=cfg, history=hist), f, indent=1)
