@@ -106,12 +106,13 @@ def test_dropin_surface_is_differentiable(smm):
         assert float((a.cpu() - b).abs().max()) <= 1e-7 * max(float(b.abs().max()), 1e-6)
 
 
-def test_graphed_trainer_trains_and_is_faster():
+@pytest.mark.parametrize('method', ['svae-cvi', 'svae-cvi-smm'])
+def test_graphed_trainer_trains_and_is_faster(method):
     """The CUDA-graph form of the training iteration: same behaviour (ELBO improves, MSE falls) at a fraction of the
     per-iteration time of the eager trainer."""
     import time
     from vmp_for_svae_b200 import experiments as ex
-    cfg = dict(dataset='pinwheel', method='svae-cvi', lr=0.01, lrcvi=0.1, decay_rate=0.95, K=10, L=2, U=40, seed=0)
+    cfg = dict(dataset='pinwheel', method=method, lr=0.01, lrcvi=0.1, decay_rate=0.95, K=10, L=2, U=40, DoF=5, seed=0)
     X_tr, _, X_te, l_te = ex.make_dataset('pinwheel')
     dev = torch.device('cuda', 0)
     y_tr = torch.as_tensor(X_tr, dtype=torch.float32, device=dev)

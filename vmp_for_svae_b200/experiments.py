@@ -260,15 +260,14 @@ class GraphedSVAETrainer(SVAETrainer):
     shapes (64-100 points, K = 10) are launch-bound, ~40 small launches per iteration.  Everything an iteration needs
     is device-resident: minibatch indices, noise and Gumbel uniforms come from torch's graph-safe generator, the CVI
     step size is a device scalar multiplied by decay^(1/1000) each replay, the upstream scalar of the regulariser
-    reaches the reverse kernel as a device pointer.  GMM variant ('svae-cvi')."""
+    reaches the reverse kernel as a device pointer.  Both variants ('svae-cvi', 'svae-cvi-smm')."""
 
     def __init__(self, config, y_train, size_minibatch, device='cuda', nb_samples=10, stddev_init_nn=0.01,
                  decoder_type='standard'):
         super().__init__(config, y_train.shape[1], device=device, nb_samples=nb_samples, stddev_init_nn=stddev_init_nn,
                          decoder_type=decoder_type)
-        assert not self.smm, 'graphed trainer: GMM variant only'
         self.y_train, self.M = y_train, int(size_minibatch)
-        params = list(self.encoder.parameters()) + list(self.decoder.parameters()) + self.phi_gmm
+        params = [p for grp in self.opt.param_groups for p in grp['params']]     # incl. mu_k, L_k of the SMM variant
         self.opt = torch.optim.Adam(params, lr=config['lr'], eps=1e-8, capturable=True)
         self.rho = torch.full((1,), float(config['lrcvi']), dtype=torch.float64, device=self.dev)
         self.decay = float(config.get('decay_rate', 1.0)) ** (1.0 / 1000.0)
@@ -283,13 +282,17 @@ class GraphedSVAETrainer(SVAETrainer):
         u = torch.rand(N, K, device=self.dev)
         eta1, eta2d = self.encoder(y)
         x_k, log_r, reg, acc, x_samp, z = local_step_autograd(
-            eta1, eta2d, self.phi_gmm[0], self.phi_gmm[1], self.phi_gmm[2], core.theta_prepare_gauss(self.theta), S,
-            noise=noise, u=u, full=True)
+            eta1, eta2d, self.phi_gmm[0], self.phi_gmm[1], self.phi_gmm[2], self.theta_record(), S,
+            den_mode=core.DEN_STUDENT if self.smm else core.DEN_GAUSS, noise=noise, u=u, full=True)
         neg_rec = decoder_loglike_autograd(y, self.decoder(x_k), torch.exp(log_r), self.decoder_type)
         elbo = neg_rec - reg
         (-elbo).backward()
-        stats = core.suffstats(x_samp, log_r.detach(), r_is_log=True)
-        core.ng_update(stats, self.rho, self.prior, self.theta)
+        if self.smm:                                                     # experiments.py:255-256 : alpha only
+            stats = core.suffstats(torch.zeros(N, 1, device=self.dev), log_r.detach(), r_is_log=True)
+            core.ng_update(stats, self.rho, self.prior, [self.alpha], only_alpha=True)
+        else:
+            stats = core.suffstats(x_samp, log_r.detach(), r_is_log=True)
+            core.ng_update(stats, self.rho, self.prior, self.theta)
         self.opt.step()
         self.rho.mul_(self.decay)                                       # experiments.py:143-147
         return torch.stack([elbo.detach(), neg_rec.detach(), reg.detach(), acc[3].to(elbo.dtype)])
@@ -327,7 +330,6 @@ def run_experiment(config, nb_iters=2000, size_minibatch=64, measurement_freq=50
     y_tr = torch.as_tensor(X_tr, dtype=torch.float32, device=dev)
     y_te = torch.as_tensor(X_te, dtype=torch.float32, device=dev)
     lbl_te = torch.as_tensor(l_te, device=dev)
-    graphed = graphed and 'smm' not in config['method']
     if graphed:
         tr = GraphedSVAETrainer(config, y_tr, size_minibatch, device=dev, nb_samples=nb_samples).capture()
     else:
@@ -364,7 +366,7 @@ if __name__ == '__main__':
     ap.add_argument('--method', default='svae-cvi')
     ap.add_argument('--iters', type=int, default=2000)
     ap.add_argument('--out', default=None)
-    ap.add_argument('--graphed', action='store_true', help='replay the iteration from a CUDA graph (GMM variant)')
+    ap.add_argument('--graphed', action='store_true', help='replay the iteration from a CUDA graph')
     a = ap.parse_args()
     pin = a.dataset != 'auto-like'
     cfg = create_schedule({'dataset': a.dataset, 'method': a.method, 'lr': [0.01 if pin else 0.0003],
