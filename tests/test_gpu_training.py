@@ -133,4 +133,4 @@ def test_graphed_trainer_trains_and_is_faster(method):
     assert last['mse'] < 0.5 * first['mse'], (first, last)
     assert abs(float(tr.rho) - 0.1 * 0.95 ** (tr.global_step / 1000.0)) < 1e-9
     print('graphed training iteration: %.3f ms' % ms)
-    assert ms < 1.5, ms
+    assert ms < 2.0, ms            # eager iteration: 2.2-2.6 ms; measured replay: 0.52 ms (GMM), 0.65 ms (SMM)
