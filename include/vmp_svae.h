@@ -79,6 +79,10 @@ int vmp_theta_prepare_student_f64(int K, int D, const double* alpha, const doubl
  *      noise[N,K,D,S] or NULL           injected raw noise (svae.py:113-114 layout); NULL -> Philox(seed)
  *      gumbel_u[N,K] or NULL            injected uniforms of the categorical draw z_n = argmax_k(log r_nk -
  *                                       log(-log u_nk)) (tf.multinomial's GPU algorithm); NULL -> Philox(seed)
+ *      point_offset                     global index of point 0 of this call: the in-kernel Philox streams are keyed by
+ *                                       the GLOBAL pair index (point_offset + n) * K + k, so a batch sharded across
+ *                                       ranks (data.py:174-175) or processed in host chunks draws exactly what one call
+ *                                       over the whole batch draws.  Ignored for injected noise / gumbel_u.
  *      x_in[N,K,S,D] or NULL            evaluate these samples instead of drawing (svae.compute_elbo called with
  *                                       caller-supplied x_k_samps); eps is recovered as a + L^T (x - mu1)
  * out: log_r[N,K]                       normalised log q(z|y)         (may not be NULL)
@@ -88,16 +92,17 @@ int vmp_theta_prepare_student_f64(int K, int D, const double* alpha, const doubl
  *                                       regulariser = mean_s sum r (num - den), number of non-PD pivots   */
 int vmp_svae_local_step_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                             const float* phi_rec, const float* theta_rec, int den_mode,
-                            const float* noise, const float* gumbel_u, uint64_t seed, const float* x_in,
-                            float* log_r, float* x_sample, int32_t* z, float* x_k_samples,
+                            const float* noise, const float* gumbel_u, uint64_t seed, int64_t point_offset,
+                            const float* x_in, float* log_r, float* x_sample, int32_t* z, float* x_k_samples,
                             double* elbo_acc, void* workspace, size_t workspace_bytes, void* stream);
 int vmp_svae_local_step_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
                             const double* phi_rec, const double* theta_rec, int den_mode,
-                            const double* noise, const double* gumbel_u, uint64_t seed, const double* x_in,
-                            double* log_r, double* x_sample, int32_t* z, double* x_k_samples,
+                            const double* noise, const double* gumbel_u, uint64_t seed, int64_t point_offset,
+                            const double* x_in, double* log_r, double* x_sample, int32_t* z, double* x_k_samples,
                             double* elbo_acc, void* workspace, size_t workspace_bytes, void* stream);
-/* Caller-provided scratch for the step (staged per-component records of the fp32 fast path, D in {16,32,64});
- * without it (NULL / too small) the generic thread-per-pair kernels run instead.                       */
+/* Caller-provided scratch for the step: the staged per-component records of the fp32 group engine (9 <= D <= 64 runs
+ * in an engine of dimension 16 / 32 / 64).  Without it (NULL / too small), for D <= 8, for fp64 and for caller-supplied
+ * samples (x_in) the thread-per-pair kernels run instead.  No environment variable selects anything.     */
 size_t vmp_svae_local_step_workspace_bytes(int K, int D);
 
 /* ---- reverse pass of the fused local step ---------------------------------------------------------------
@@ -110,7 +115,7 @@ size_t vmp_svae_local_step_workspace_bytes(int K, int D);
  * (device scalar, may be NULL) overrides greg so that no host synchronisation is needed (CUDA-graph capture).
  * theta_rec_bar[K, vmp_theta_record_len(D)] (may be NULL) receives the gradient w.r.t. the theta record (W lower | m |
  * cden, zeros): compute_elbo_smm trains mu_k, L_k of the Student-t components by gradient (svae.py:265-322 has no
- * stop_gradient on them; experiments.py:154-174).  D <= VMP_BWD_MAX_D, K <= 256.  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
+ * stop_gradient on them; experiments.py:154-174).  The in-kernel noise is keyed with point_offset 0.  D <= VMP_BWD_MAX_D, K <= 256.  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
 #define VMP_BWD_MAX_D 16
 size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D);
 int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
@@ -130,8 +135,10 @@ int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* et
 
 /* The noise the in-kernel generator uses for a given seed, written in the reference layout
  * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N,K] (either may be NULL).      */
-int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, float* noise, float* u, void* stream);
-int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, double* noise, double* u, void* stream);
+int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, int64_t point_offset, float* noise, float* u,
+                       void* stream);
+int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, int64_t point_offset, double* noise, double* u,
+                       void* stream);
 
 /* ---- responsibility-weighted sufficient statistics --------------------------------------------------
  * Replaces the reductions of gmm.m_step (gmm.py:25-46,201-227: update_Nk/xk/Sk) and smm.m_step
@@ -230,6 +237,15 @@ int vmp_gaussian_logprob_nat_f32(int64_t N, int K, int S, int D, const float* x,
                                  const float* eta2, const float* log_w, float* out, void* stream);
 int vmp_gaussian_logprob_nat_f64(int64_t N, int K, int S, int D, const double* x, const double* eta1,
                                  const double* eta2, const double* log_w, double* out, void* stream);
+
+/* Dense-natural-parameter sampling (API surface of svae.sample_x_per_comp, svae.py:95-119; the fused step never builds
+ * these tensors): for B = N*K systems, P = -2 eta2[b] = L L^T (lower Cholesky, svae.py:111),
+ * x[b,s,:] = P^-1 eta1[b] + L^-T noise[b,:,s]   (svae.py:115-118).  eta1[B,D], eta2[B,D,D], noise[B,D,S] -> x[B,S,D];
+ * non_pd (device int, may be NULL) counts systems with a non-positive pivot.  Arithmetic in double.            */
+int vmp_gaussian_sample_nat_f32(int64_t B, int D, int S, const float* eta1, const float* eta2, const float* noise,
+                                float* x, int* non_pd, void* stream);
+int vmp_gaussian_sample_nat_f64(int64_t B, int D, int S, const double* eta1, const double* eta2, const double* noise,
+                                double* x, int* non_pd, void* stream);
 
 /* FP32 pipe probe (measurement aid, not part of the reference surface): grid x 256 threads, each iters*128 FMAs as
  * scalar FFMA (packed == 0) or packed FFMA2 / fma.rn.f32x2 (packed != 0); out[grid*256] floats.  Timed by the caller. */

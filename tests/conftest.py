@@ -53,7 +53,8 @@ def regen_decoder(g):
     return np.sign(y), (np.zeros((N, K, S, dobs)), rs.randn(N, K, S, dobs)), decoder
 
 
-SVAE_CASES = ['svae_c1', 'svae_c2', 'svae_init', 'svae_d8', 'svae_d16', 'svae_d32', 'svae_d64']
+SVAE_CASES = ['svae_c1', 'svae_c2', 'svae_init', 'svae_d8', 'svae_d16', 'svae_d32', 'svae_d64', 'svae_d32_overlap',
+              'svae_d64_overlap']
 
 
 def losses_inputs(seed, N, K, S, D, C=4):

@@ -64,7 +64,8 @@ def synth_decoder_outputs(seed, N, K, S, dobs, decoder):
     return np.sign(y), (np.zeros((N, K, S, dobs)), rs.randn(N, K, S, dobs))
 
 
-def svae_case(tf, M, name, K, D, N, S, seed, rho, dobs=3, decoder='standard', keep_big=True, perturb=True):
+def svae_case(tf, M, name, K, D, N, S, seed, rho, dobs=3, decoder='standard', keep_big=True, perturb=True,
+              overlap=None):
     svae = M['svae']
     tf.reset_default_graph()
     del tf.rng_log[:]
@@ -78,16 +79,27 @@ def svae_case(tf, M, name, K, D, N, S, seed, rho, dobs=3, decoder='standard', ke
         # move phi_gmm / theta away from their symmetric initial values so that every code path
         # (off-diagonal L, non-trivial A, b) is exercised
         mu_k, L_k, pi_k = phi_gmm
-        mu_k.a[...] = mu_k.a + 0.3 * rs.randn(K, D)
-        L_k.a[...] = L_k.a + 0.2 * rs.randn(K, D, D)
+        mu_k.a[...] = mu_k.a + (0.3 if overlap is None else 0.1) * rs.randn(K, D)
+        L_k.a[...] = L_k.a + (0.2 if overlap is None else 0.1 / D ** 0.5) * rs.randn(K, D, D)
         pi_k.a[...] = pi_k.a + 0.1 * rs.randn(K)
         xs0 = 2.0 * rs.randn(4 * K + 7, D)
         r0 = rs.dirichlet(np.ones(K), size=xs0.shape[0])
         star0 = svae.m_step(prior, tf.constant(xs0), tf.constant(r0))
         svae.update_gmm_params(theta, star0, 0.5)
+    if overlap is not None:
+        # overlapping recognition components (the D >= 32 cases above have one-hot responsibilities):
+        # shrink the components' eta1 towards 0 so that their centres P2^-1 eta1 crowd together
+        phi_gmm[0].a[...] = overlap * phi_gmm[0].a
     theta_before = [A(t).copy() for t in theta]
     phi_gmm_np = [A(t).copy() for t in phi_gmm]
-    eta1, eta2d = synth_encoder_outputs(rs, N, D, K, scale=2.0)
+    if overlap is None:
+        eta1, eta2d = synth_encoder_outputs(rs, N, D, K, scale=2.0)
+    else:
+        _, eta2_phi2, _ = svae.unpack_recognition_gmm(phi_gmm)
+        centres = np.linalg.solve(-2.0 * A(eta2_phi2), A(phi_gmm[0])[..., None])[..., 0]
+        eta2d = -0.5 * np.logaddexp(0.0, rs.randn(N, D))
+        mu1 = centres[rs.randint(0, K, size=N)] + 0.3 * rs.randn(N, D)
+        eta1 = mu1 * (-2.0 * eta2d)
     x_k, log_r, phi_tilde, dbg = svae.e_step((tf.constant(eta1), tf.constant(eta2d)), phi_gmm, S, seed=seed)
     noise = take_log(tf)[0][1]                                  # [N,K,D,S]
     xs_all = svae.subsample_x(x_k, log_r, seed)
@@ -121,7 +133,9 @@ def svae_case(tf, M, name, K, D, N, S, seed, rho, dobs=3, decoder='standard', ke
     else:
         out.update(x_k_every4=A(x_k)[::4])
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
-    print(name, 'elbo', float(A(elbo)), 'N_k', star_np[0][:4])
+    r = np.exp(A(log_r))
+    print(name, 'elbo', float(A(elbo)), 'N_k', star_np[0][:4], 'mean entropy of r %.3f' % float(-(r * A(log_r)).sum(1).mean()),
+          'rows with max r < 0.99: %.2f' % float((r.max(1) < 0.99).mean()))
 
 
 def svae_smm_case(tf, M, name, K, D, N, S, seed, rho, dof):
@@ -312,6 +326,15 @@ if __name__ == '__main__':
     tf.set_float(np.float64)
     if '--losses-only' in sys.argv:
         losses_cases(tf, M)
+        sys.exit(0)
+    if '--overlap-only' not in sys.argv:
+        main_cases = True
+    else:
+        main_cases = False
+    # non-degenerate responsibilities at D = 32 / 64 (round 2)
+    svae_case(tf, M, 'svae_d64_overlap', K=8, D=64, N=24, S=1, seed=6, rho=0.2, keep_big=False, overlap=0.2)
+    svae_case(tf, M, 'svae_d32_overlap', K=16, D=32, N=32, S=2, seed=7, rho=0.2, keep_big=False, overlap=0.3)
+    if not main_cases:
         sys.exit(0)
     svae_case(tf, M, 'svae_c1', K=10, D=2, N=100, S=10, seed=0, rho=0.1)
     svae_case(tf, M, 'svae_c2', K=10, D=6, N=274, S=10, seed=0, rho=0.2, dobs=6, keep_big=False)

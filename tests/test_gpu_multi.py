@@ -1,7 +1,7 @@
 """Two-rank NCCL run of the sharded step on real GPUs (skipped when fewer than 2 devices are visible): points are
 sharded contiguously, the packed statistics are all-reduced once, and every rank must end with the theta a single
-GPU computes from the full batch (same in-kernel noise stream: the Philox counters are global point indices only
-on one GPU, so the comparison uses injected noise)."""
+GPU computes from the full batch — with injected noise AND with the in-kernel Philox stream (keyed by the global
+pair index: every rank passes the same seed and its shard's point_offset)."""
 import os
 import subprocess
 import sys
@@ -46,6 +46,17 @@ assert torch.equal(o['log_r'], of['log_r'][a:b]) and torch.equal(o['z'], of['z']
 for x, y in zip(th, th_full):
     torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
 torch.testing.assert_close(o['elbo_acc'][:3], acc_full[:3], rtol=1e-9, atol=1e-6)
+# the same with in-kernel noise: seed shared by all ranks, stream keyed by the global point index
+th_full2 = [t.clone() for t in theta]
+of2 = SVAEStep(N, K, D, S, dtype=dt, device=dev, use_dist=False).step((eta1, eta2d), phi_gmm, th_full2, prior, 0.3, seed=99)
+th2 = [t.clone() for t in theta]
+st2 = SVAEStep(b - a, K, D, S, dtype=dt, device=dev, point_offset=a)
+o2 = st2.step((eta1[a:b].contiguous(), eta2d[a:b].contiguous()), phi_gmm, th2, prior, 0.3, seed=99)
+torch.cuda.synchronize()
+assert torch.equal(o2['log_r'], of2['log_r'][a:b]) and torch.equal(o2['z'], of2['z'][a:b])
+assert torch.equal(o2['x_sample'], of2['x_sample'][a:b])
+for x, y in zip(th2, th_full2):
+    torch.testing.assert_close(x, y, rtol=1e-6, atol=1e-6)
 # replicas are bit-identical after the all-reduce
 for t in th:
     other = t.clone()

@@ -47,6 +47,32 @@ def test_product_does_not_import_oracle():
                 assert 'from oracle' not in src and 'import oracle' not in src, f
 
 
+def test_product_has_no_runtime_switches():
+    """north_star: no multi-backend dispatch — nothing in the product library selects a code path from the environment."""
+    csrc = os.path.join(ROOT, 'vmp_for_svae_b200', 'csrc')
+    for f in os.listdir(csrc):
+        assert 'getenv' not in open(os.path.join(csrc, f)).read(), f
+
+
+def test_uniform_mapping_never_hits_0_or_1(tmp_path):
+    """common.cuh::u32_to_unit on the host (nvcc host compile): the extreme counters map strictly inside (0,1) and the
+    mapping is exact in fp32 (the 24-bit form rounded 0xFFFFFFFF to 1.0 -> Gumbel = +inf)."""
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    src = tmp_path / 'u.cu'
+    src.write_text('#include <cstdio>\n#include "%s"\nint main(){ unsigned v[5]={0u,1u,0x7fffffffu,0xfffffe00u,0xffffffffu};'
+                   'for(int i=0;i<5;++i) printf("%%.17g\\n",(double)vmp::u32_to_unit(v[i])); return 0; }\n'
+                   % os.path.join(ROOT, 'vmp_for_svae_b200', 'csrc', 'common.cuh'))
+    exe = tmp_path / 'u'
+    subprocess.check_call([nvcc, '-std=c++17', '-o', str(exe), str(src)], stderr=subprocess.DEVNULL)
+    vals = [float(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert vals[0] == 0.5 / 8388608 and vals[1] == vals[0]
+    assert vals[4] == (8388607 + 0.5) / 8388608 and vals[4] < 1.0 and vals[0] > 0.0
+    assert all(0.0 < v < 1.0 for v in vals) and vals == sorted(vals)
+    assert np.isfinite(-np.log(-np.log(np.float32(vals[4])))) and np.isfinite(-np.log(-np.log(np.float32(vals[0]))))
+
+
 def test_shard_range_partitions():
     from vmp_for_svae_b200.dist import shard_range
     for n in (0, 1, 7, 100, 1 << 20):

@@ -18,12 +18,12 @@ _SIGS_T = {
     'vmp_phi_prepare': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_theta_prepare_gauss': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_theta_prepare_student': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
-    'vmp_svae_local_step': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_u64, c_ptr,
-                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr],
+    'vmp_svae_local_step': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_u64, c_i64,
+                            c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr],
     'vmp_svae_local_step_bwd': [c_i64, c_int, c_int, c_int] + [c_ptr] * 7 + [c_int, c_ptr, c_u64, c_ptr, c_ptr, c_ptr,
                                                                                c_dbl, c_ptr] + [c_ptr] * 6 +
                                [c_ptr, ctypes.c_size_t, c_ptr],
-    'vmp_fill_noise': [c_i64, c_int, c_int, c_int, c_u64, c_ptr, c_ptr, c_ptr],
+    'vmp_fill_noise': [c_i64, c_int, c_int, c_int, c_u64, c_i64, c_ptr, c_ptr, c_ptr],
     'vmp_suffstats': [c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr],
     'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_ptr, c_int] + [c_ptr] * 15 + [c_ptr],
     'vmp_mixture_mstep': [c_int, c_int, c_int, c_ptr] + [c_ptr] * 12 + [c_ptr],
@@ -33,6 +33,7 @@ _SIGS_T = {
     'vmp_decoder_loglike_bwd': [c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr,
                                 c_ptr, c_ptr],
     'vmp_decoder_metrics': [c_i64, c_int, c_int, c_int, c_int] + [c_ptr] * 8 + [c_ptr],
+    'vmp_gaussian_sample_nat': [c_i64, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_gaussian_logprob_nat': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
 }
 _SIGS = {
@@ -56,11 +57,12 @@ def lib_path():
 
 
 def load(build_if_missing=True):
-    """Load (building first if the .so is absent or stale and nvcc is available)."""
+    """Load (building first if the .so is absent or stale and nvcc is available).  _build.build() is incremental: with
+    an up-to-date .so it only compares mtimes; on a box without nvcc the shipped .so is used as is."""
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing and (not os.path.exists(_LIB_PATH)):
+    if build_if_missing and (not os.path.exists(_LIB_PATH) or _build.nvcc_available()):
         _build.build()
     if not os.path.exists(_LIB_PATH):
         raise VmpError('libvmp_svae.so is missing: run `python -m vmp_for_svae_b200._build` (needs nvcc); '
@@ -104,11 +106,17 @@ def stream_ptr(device=None):
     return c_ptr(torch.cuda.current_stream(device).cuda_stream)
 
 
-def call(name, dtype, *args):
-    """Call the _f32/_f64 flavour of `name`; non-zero status raises."""
+def call(name, dtype, *args, device=None):
+    """Call the _f32/_f64 flavour of `name`; non-zero status raises.  `device`: the CUDA device of the tensors — the
+    launch is issued with that device current (the stream pointer passed in `args` belongs to it)."""
     lib = load()
     fn = getattr(lib, name + suffix(dtype))
-    rc = fn(*args)
+    if device is not None and device.type == 'cuda' and device.index is not None \
+            and device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
     if rc != 0:
         if rc < 0:
             why = {-1: 'invalid argument', -2: 'latent dimension outside 1..64', -3: 'bad mode'}.get(rc, 'error')

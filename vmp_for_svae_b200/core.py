@@ -26,7 +26,7 @@ def phi_prepare(eta1_phi2, L_raw, pi_raw, out=None):
     pi_raw = _chk(pi_raw, (K,), dt, 'pi_k_raw')
     plen = _lib.record_lens(D)[0]
     rec = out if out is not None else torch.empty(K, plen, dtype=dt, device=dev)
-    _lib.call('vmp_phi_prepare', dt, K, D, ptr(eta1_phi2), ptr(L_raw), ptr(pi_raw), ptr(rec), stream_ptr(dev))
+    _lib.call('vmp_phi_prepare', dt, K, D, ptr(eta1_phi2), ptr(L_raw), ptr(pi_raw), ptr(rec), stream_ptr(dev), device=dev)
     return rec
 
 
@@ -40,7 +40,7 @@ def theta_prepare_gauss(theta, out=None):
     tlen = _lib.record_lens(D)[1]
     rec = out if out is not None else torch.empty(K, tlen, dtype=dt, device=dev)
     _lib.call('vmp_theta_prepare_gauss', dt, K, D, ptr(alpha), ptr(A), ptr(b), ptr(beta), ptr(v_hat), ptr(rec),
-              stream_ptr(dev))
+              stream_ptr(dev), device=dev)
     return rec
 
 
@@ -54,7 +54,7 @@ def theta_prepare_student(theta, out=None):
     tlen = _lib.record_lens(D)[1]
     rec = out if out is not None else torch.empty(K, tlen, dtype=dt, device=dev)
     _lib.call('vmp_theta_prepare_student', dt, K, D, ptr(alpha), ptr(mu), ptr(L_raw), ptr(dof), ptr(rec),
-              stream_ptr(dev))
+              stream_ptr(dev), device=dev)
     return rec
 
 
@@ -67,9 +67,11 @@ def local_step_workspace(K, D, device):
 
 def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise=None, u=None, seed=0, x_in=None,
                want_x_sample=True, want_z=True, materialize_x_k=False, log_r=None, x_sample=None, z=None,
-               elbo_acc=None, workspace=None):
+               elbo_acc=None, workspace=None, point_offset=0, use_engine=True):
     """The fused local step.  Returns dict(log_r, x_sample, z, x_k_samples, elbo_acc[4] double).
-    u: uniforms[N,K] of the Gumbel-max categorical draw (None -> in-kernel Philox keyed by `seed`)."""
+    u: uniforms[N,K] of the Gumbel-max categorical draw (None -> in-kernel Philox keyed by `seed`).
+    point_offset: global index of eta1[0] (shards / host chunks draw the noise of the whole batch).
+    use_engine=False withholds the workspace, i.e. runs the thread-per-pair kernels (tests compare the two)."""
     N, D = eta1.shape
     K = phi_rec.shape[0]
     dt, dev = eta1.dtype, eta1.device
@@ -90,12 +92,14 @@ def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise
     x_k = torch.empty(N, K, S, D, dtype=dt, device=dev) if materialize_x_k else None
     if elbo_acc is None:
         elbo_acc = torch.zeros(4, dtype=torch.float64, device=dev)
-    if workspace is None and dt == torch.float32 and x_in is None:
+    if not use_engine:
+        workspace = None
+    elif workspace is None and dt == torch.float32 and x_in is None:
         workspace = local_step_workspace(K, D, dev)
     wbytes = workspace.numel() * workspace.element_size() if workspace is not None else 0
     _lib.call('vmp_svae_local_step', dt, N, K, D, S, ptr(eta1), ptr(eta2_diag), ptr(phi_rec), ptr(theta_rec),
-              int(den_mode), ptr(noise), ptr(u), int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(x_in), ptr(log_r), ptr(x_sample),
-              ptr(z), ptr(x_k), ptr(elbo_acc), ptr(workspace), wbytes, stream_ptr(dev))
+              int(den_mode), ptr(noise), ptr(u), int(seed) & 0xFFFFFFFFFFFFFFFF, int(point_offset), ptr(x_in), ptr(log_r), ptr(x_sample),
+              ptr(z), ptr(x_k), ptr(elbo_acc), ptr(workspace), wbytes, stream_ptr(dev), device=dev)
     return dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=x_k, elbo_acc=elbo_acc)
 
 
@@ -128,15 +132,16 @@ def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, thet
     _lib.call('vmp_svae_local_step_bwd', dt, N, K, D, S, ptr(eta1), ptr(eta2_diag), ptr(eta1_phi2), ptr(L_raw),
               ptr(pi_raw), ptr(phi_rec), ptr(theta_rec), int(den_mode), ptr(noise), int(seed) & 0xFFFFFFFFFFFFFFFF,
               ptr(log_r), ptr(gx), ptr(glr), float(greg), ptr(greg_dev), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(out[3]),
-              ptr(out[4]), ptr(th_bar), ptr(work), nbytes, stream_ptr(dev))
+              ptr(out[4]), ptr(th_bar), ptr(work), nbytes, stream_ptr(dev), device=dev)
     return tuple(out) + ((th_bar,) if want_theta_rec_bar else ())
 
 
-def fill_noise(N, K, D, S, seed, dtype, device, want_noise=True, want_u=True):
+def fill_noise(N, K, D, S, seed, dtype, device, want_noise=True, want_u=True, point_offset=0):
+    device = torch.device(device)
     noise = torch.empty(N, K, D, S, dtype=dtype, device=device) if want_noise else None
     u = torch.empty(N, K, dtype=dtype, device=device) if want_u else None
-    _lib.call('vmp_fill_noise', dtype, N, K, D, S, int(seed) & 0xFFFFFFFFFFFFFFFF, ptr(noise), ptr(u),
-              stream_ptr(device))
+    _lib.call('vmp_fill_noise', dtype, N, K, D, S, int(seed) & 0xFFFFFFFFFFFFFFFF, int(point_offset), ptr(noise), ptr(u),
+              stream_ptr(device), device=device)
     return noise, u
 
 
@@ -151,7 +156,7 @@ def suffstats(x, r, r_is_log=False, u_nk=None, stats=None):
     slen = _lib.record_lens(D)[2]
     if stats is None:
         stats = torch.zeros(K, slen, dtype=torch.float64, device=dev)
-    _lib.call('vmp_suffstats', dt, N, K, D, ptr(x), ptr(r), int(bool(r_is_log)), ptr(u_nk), ptr(stats), stream_ptr(dev))
+    _lib.call('vmp_suffstats', dt, N, K, D, ptr(x), ptr(r), int(bool(r_is_log)), ptr(u_nk), ptr(stats), stream_ptr(dev), device=dev)
     return stats
 
 
@@ -169,7 +174,7 @@ def ng_update(stats, rho, prior, theta, only_alpha=False, want_star=False):
         D = (stats.shape[1] and int(round((-1 + (1 + 4 * (stats.shape[1] - 2)) ** 0.5) / 2)))
         star = [torch.empty_like(alpha)] if want_star else [None]
         _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), ptr(rho_dev), 1, ptr(prior[0].contiguous()), None, None, None,
-                  None, ptr(alpha), None, None, None, None, ptr(star[0]), None, None, None, None, stream_ptr(dev))
+                  None, ptr(alpha), None, None, None, None, ptr(star[0]), None, None, None, None, stream_ptr(dev), device=dev)
         return star if want_star else None
     D = theta[2].shape[1]
     for t in theta:
@@ -178,7 +183,7 @@ def ng_update(stats, rho, prior, theta, only_alpha=False, want_star=False):
     star = [torch.empty_like(t) for t in theta] if want_star else [None] * 5
     _lib.call('vmp_ng_update', dt, K, D, ptr(stats), float(rho), ptr(rho_dev), 0, ptr(p[0]), ptr(p[1]), ptr(p[2]), ptr(p[3]), ptr(p[4]),
               ptr(theta[0]), ptr(theta[1]), ptr(theta[2]), ptr(theta[3]), ptr(theta[4]),
-              ptr(star[0]), ptr(star[1]), ptr(star[2]), ptr(star[3]), ptr(star[4]), stream_ptr(dev))
+              ptr(star[0]), ptr(star[1]), ptr(star[2]), ptr(star[3]), ptr(star[4]), stream_ptr(dev), device=dev)
     return star if want_star else None
 
 
@@ -190,7 +195,7 @@ def mixture_mstep(stats, D, is_smm, alpha_0, beta_0, m_0, C_0, v_0):
     e = lambda *s: torch.empty(*s, dtype=dt, device=dev)
     out = (e(K), e(K), e(K, D), e(K, D, D), e(K), e(K, D), e(K, D, D))
     _lib.call('vmp_mixture_mstep', dt, K, D, int(bool(is_smm)), ptr(stats), ptr(alpha_0), ptr(beta_0), ptr(m_0), ptr(C_0),
-              ptr(v_0), *[ptr(o) for o in out], stream_ptr(dev))
+              ptr(v_0), *[ptr(o) for o in out], stream_ptr(dev), device=dev)
     return out
 
 
@@ -210,7 +215,7 @@ def mixture_estep(x, alpha_k, beta_k, m_k, P_k, v_k, kappa_k=None, missing_mask=
     pi = torch.empty(K, dtype=dt, device=dev)
     work = torch.empty(K, dtype=dt, device=dev)
     _lib.call('vmp_mixture_estep', dt, N, K, D, ptr(x), ptr(alpha_k), ptr(beta_k), ptr(m_k), ptr(P_k), ptr(v_k),
-              ptr(kappa_k), ptr(missing_mask), ptr(r), ptr(u_out), ptr(pi), ptr(work), stream_ptr(dev))
+              ptr(kappa_k), ptr(missing_mask), ptr(r), ptr(u_out), ptr(pi), ptr(work), stream_ptr(dev), device=dev)
     return r, u_out, pi
 
 
@@ -223,7 +228,7 @@ def spd_inverse(mats, want_inv=True, want_logdet=True):
     B = flat.shape[0]
     inv = torch.empty_like(flat) if want_inv else None
     ld = torch.empty(B, dtype=dt, device=dev) if want_logdet else None
-    _lib.call('vmp_spd_inverse', dt, B, D, ptr(flat), ptr(inv), ptr(ld), stream_ptr(dev))
+    _lib.call('vmp_spd_inverse', dt, B, D, ptr(flat), ptr(inv), ptr(ld), stream_ptr(dev), device=dev)
     return (inv.reshape(*lead, D, D) if want_inv else None), (ld.reshape(lead) if want_logdet else None)
 
 
@@ -236,7 +241,7 @@ def decoder_loglike(y, means, out2, w, mode):
         means = _chk(means, (N, K, S, Dobs), dt, 'means')
     acc = torch.zeros(1, dtype=torch.float64, device=dev)
     _lib.call('vmp_decoder_loglike', dt, N, K, S, Dobs, int(mode), ptr(y), ptr(means), ptr(out2), ptr(w), ptr(acc),
-              stream_ptr(dev))
+              stream_ptr(dev), device=dev)
     return acc
 
 
@@ -251,7 +256,7 @@ def decoder_loglike_backward(y, means, out2, w, mode, scale):
         g_means = torch.empty_like(means)
     g_out2, g_w = torch.empty_like(out2), torch.empty_like(w)
     _lib.call('vmp_decoder_loglike_bwd', dt, N, K, S, Dobs, int(mode), ptr(y), ptr(means), ptr(out2), ptr(w),
-              float(scale), ptr(g_means), ptr(g_out2), ptr(g_w), stream_ptr(dev))
+              float(scale), ptr(g_means), ptr(g_out2), ptr(g_w), stream_ptr(dev), device=dev)
     return g_means, g_out2, g_w
 
 
@@ -269,7 +274,7 @@ def decoder_metrics(y, means, out2, mode, target=None, mask=None, log_w_nks=None
     sq = torch.empty(N, K, dtype=dt, device=dev) if want_sq else None
     lse = torch.empty(N, K, dtype=dt, device=dev) if want_lse else None
     _lib.call('vmp_decoder_metrics', dt, N, K, S, Dobs, int(mode), ptr(y), ptr(target), ptr(means), ptr(out2), ptr(mask),
-              ptr(log_w_nks), ptr(sq), ptr(lse), stream_ptr(dev))
+              ptr(log_w_nks), ptr(sq), ptr(lse), stream_ptr(dev), device=dev)
     return sq, lse
 
 
@@ -288,5 +293,20 @@ def gaussian_logprob_nat(x, eta1, eta2, log_w=None, per_samp=False):
     if log_w is not None:
         log_w = _chk(log_w, (K,), dt, 'log weights')
     _lib.call('vmp_gaussian_logprob_nat', dt, N, K, S, D, ptr(x), ptr(eta1), ptr(eta2), ptr(log_w), ptr(out),
-              stream_ptr(dev))
+              stream_ptr(dev), device=dev)
     return out
+
+
+def gaussian_sample_nat(eta1, eta2, noise):
+    """x[N,K,S,D] = P^-1 eta1 + L^-T noise for dense eta1[N,K,D(,1)], eta2[N,K,D,D], noise[N,K,D,S] (svae.py:95-119).
+    Returns (x, non_pd) with non_pd a device int32 count of non-positive-definite systems."""
+    N, K, D, _ = eta2.shape
+    S = noise.shape[-1]
+    dt, dev = eta2.dtype, eta2.device
+    eta1 = _chk(eta1.reshape(N, K, D), (N, K, D), dt, 'eta1'); eta2 = _chk(eta2, (N, K, D, D), dt, 'eta2')
+    noise = _chk(noise, (N, K, D, S), dt, 'noise')
+    x = torch.empty(N, K, S, D, dtype=dt, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.call('vmp_gaussian_sample_nat', dt, N * K, D, S, ptr(eta1), ptr(eta2), ptr(noise), ptr(x), ptr(bad),
+              stream_ptr(dev), device=dev)
+    return x, bad

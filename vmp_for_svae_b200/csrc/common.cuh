@@ -93,8 +93,9 @@ struct Philox {
     }
 };
 
-// uniform in (0,1): 24 random bits, never 0 or 1 (safe for log / Box-Muller and for u*total < total)
-__device__ __forceinline__ float u32_to_unit(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+// uniform in (0,1): 23 random bits at the bin centres (k + 1/2) / 2^23 — every value is exactly representable in fp32
+// (k + 1/2 needs 24 significant bits), so the result is never 0 or 1 (safe for log / Box-Muller / Gumbel)
+__host__ __device__ __forceinline__ float u32_to_unit(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 // four standard normals for (pair, sample s, dims 4q..4q+3) — the definition of the in-kernel noise stream
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t pair, uint32_t s, uint32_t q) {

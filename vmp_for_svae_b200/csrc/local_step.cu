@@ -2,19 +2,17 @@
 // and the generic thread-per-pair kernels.
 //
 // Two implementations of the same arithmetic (pair_math.cuh states it):
-//   * fast  (local_step_fast.cuh): fp32, D in {16, 32, 64}: register-resident group engine, TMA-staged records,
-//           online Gumbel-max selection — the path bench.py measures;
-//   * generic (this file): any D <= 64, fp32/fp64, one thread per (point, component) pair; D <= 8 fully unrolled in
-//           registers (the C1-C3 shapes), larger D through local memory.  Kernel A computes scores / samples / ELBO
+//   * engine (local_step_fast.cuh): fp32, 9 <= D <= 64: register-resident group engine of dimension 16 / 32 / 64 (the
+//           caller's D is embedded with an identity block), TMA-staged records, online Gumbel-max selection — the path
+//           bench.py measures.  Taken whenever the caller passes the workspace the staged records need;
+//   * generic (this file): fp64, D <= 8, caller-supplied samples (x_in), or no workspace: one thread per
+//           (point, component) pair; D <= 8 fully unrolled in registers (the C1-C3 shapes), larger D through local memory.  Kernel A computes scores / samples / ELBO
 //           terms and the per-point log-sum-exp; kernel B draws z_n by Gumbel-max from log_r and re-evaluates the
 //           selected pair for x[n, z_n, 0].
 // The categorical draw follows tf.multinomial's GPU kernel (multinomial_op_gpu.cu.cc): z = argmax_k(logit_k + G_k),
 // G_k = -log(-log(u_k)); u[N,K] may be injected for parity tests, otherwise Philox(seed, pair).
 #include "local_step_fast.cuh"
-#include "local_step_fast2d.cuh"
 #include "pair_math.cuh"
-
-#include <cstdlib>
 
 namespace vmp {
 
@@ -24,12 +22,14 @@ template <typename T> struct NoiseSrc {
     const T* noise;     // [N,K,D,S] or nullptr
     uint64_t seed;
     int K, D, S;
+    int64_t n_offset;   // global index of point 0: the in-kernel stream is keyed by the GLOBAL pair index
+    __device__ __forceinline__ uint64_t gpair(int64_t n, int k) const { return (uint64_t)(n + n_offset) * K + k; }
     __device__ __forceinline__ void load(int64_t n, int k, int s, T* eps) const {
-        const uint64_t pair = (uint64_t)n * K + k;
         if (noise != nullptr) {
-            const T* p = noise + pair * (uint64_t)D * S + s;
+            const T* p = noise + ((uint64_t)n * K + k) * (uint64_t)D * S + s;
             for (int i = 0; i < D; ++i) eps[i] = p[(size_t)i * S];
         } else {
+            const uint64_t pair = gpair(n, k);
             for (int q = 0; q < (D + 3) / 4; ++q) {
                 const float4 v = philox_normal4(seed, pair, (uint32_t)s, (uint32_t)q);
                 const int i = 4 * q;
@@ -145,7 +145,7 @@ select_sample_kernel(int64_t N, int K, int Drt, int S, const T* __restrict__ eta
     T best = -CUDART_INF_F;
     for (int k = 0; k < K; ++k) {
         const uint64_t pair = (uint64_t)n * K + k;
-        const T u = gum_u != nullptr ? gum_u[pair] : (T)philox_uniform_pair(nz.seed, pair);
+        const T u = gum_u != nullptr ? gum_u[pair] : (T)philox_uniform_pair(nz.seed, nz.gpair(n, k));
         const T cand = log_r[pair] + gumbel_from_uniform<T>(u);
         if (cand > best) { best = cand; z = k; }
     }
@@ -161,7 +161,8 @@ select_sample_kernel(int64_t N, int K, int Drt, int S, const T* __restrict__ eta
 }
 
 template <typename T>
-__global__ void fill_noise_kernel(int64_t N, int K, int D, int S, uint64_t seed, T* noise, T* u) {
+__global__ void fill_noise_kernel(int64_t N, int K, int D, int S, uint64_t seed, int64_t n_offset, T* noise, T* u) {
+    const uint64_t poff = (uint64_t)n_offset * K;
     const int64_t total = N * K * (int64_t)D * S;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (noise != nullptr)
@@ -169,18 +170,18 @@ __global__ void fill_noise_kernel(int64_t N, int K, int D, int S, uint64_t seed,
             const int s = (int)(e % S);
             const int d = (int)((e / S) % D);
             const int64_t pair = e / ((int64_t)S * D);
-            noise[e] = (T)philox_normal1(seed, (uint64_t)pair, (uint32_t)s, (uint32_t)d);
+            noise[e] = (T)philox_normal1(seed, (uint64_t)pair + poff, (uint32_t)s, (uint32_t)d);
         }
     if (u != nullptr)
-        for (int64_t pr = t0; pr < N * K; pr += stride) u[pr] = (T)philox_uniform_pair(seed, (uint64_t)pr);
+        for (int64_t pr = t0; pr < N * K; pr += stride) u[pr] = (T)philox_uniform_pair(seed, (uint64_t)pr + poff);
 }
 
 template <typename T, int DT>
 static int launch_generic(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* phi_rec,
                           const T* theta_rec, int den_mode, const T* noise, const T* gum_u, uint64_t seed,
-                          const T* x_in, T* log_r, T* x_sample, int32_t* z, T* x_k_samples, double* elbo_acc,
-                          cudaStream_t st) {
-    NoiseSrc<T> nz{noise, seed, K, D, S};
+                          int64_t n_offset, const T* x_in, T* log_r, T* x_sample, int32_t* z, T* x_k_samples,
+                          double* elbo_acc, cudaStream_t st) {
+    NoiseSrc<T> nz{noise, seed, K, D, S, n_offset};
     int PTS = LS_THREADS / K;
     if (PTS < 1) PTS = 1;
     const size_t smem = (size_t)3 * PTS * K * sizeof(T);
@@ -204,99 +205,77 @@ static int launch_generic(int64_t N, int K, int D, int S, const T* eta1, const T
     return VMP_OK;
 }
 
+// engine dimension for a caller dimension: 0 = no engine (D <= 8 runs the register-unrolled generic kernels)
+static int engine_dim(int D) { return D <= 8 ? 0 : D <= 16 ? 16 : D <= 32 ? 32 : 64; }
+
 static size_t fast_workspace_bytes(int K, int D) {
-    if (D != 16 && D != 32 && D != 64) return 0;
-    return sizeof(float) * (size_t)K * fast_rec_len(D);
+    const int De = engine_dim(D);
+    return De ? sizeof(float) * (size_t)K * fast_rec_len(De) : 0;
 }
 
-static bool fast_enabled() {
-    const char* e = std::getenv("VMP_FORCE_GENERIC");
-    return !(e && e[0] == '1');
-}
-static bool engine2d_enabled() {
-    const char* e = std::getenv("VMP_FAST_2D");
-    return e && e[0] == '1';
-}
-static bool tma_enabled() {
-    const char* e = std::getenv("VMP_NO_TMA");
-    return !(e && e[0] == '1');
-}
-
-// fp32 fast path when the shape qualifies; returns -100 when it does not
+// the group engine when the call qualifies (fp32, D > 8, drawn samples, workspace given); -100 when it does not
 static int try_fast(int64_t N, int K, int D, int S, const float* eta1, const float* eta2d, const float* phi_rec,
                     const float* theta_rec, int den_mode, const float* noise, const float* gum_u, uint64_t seed,
-                    const float* x_in, float* log_r, float* x_sample, int32_t* z, float* x_k_samples,
+                    int64_t n_offset, const float* x_in, float* log_r, float* x_sample, int32_t* z, float* x_k_samples,
                     double* elbo_acc, void* work, size_t work_bytes, cudaStream_t st) {
-    if (!fast_enabled() || x_in != nullptr || work == nullptr) return -100;
+    if (x_in != nullptr || work == nullptr) return -100;
+    const int De = engine_dim(D);
     const size_t need = fast_workspace_bytes(K, D);
-    if (need == 0 || work_bytes < need) return -100;
-    // lanes per pair: D/4 ("narrow", 4 rows per lane) or D/2 ("wide", 2 rows per lane: fewer registers, more warps)
-    const char* we = std::getenv("VMP_FAST_WIDE");
-    const bool wide = we ? we[0] == '1' : false;
-    size_t smem = D == 64 ? (wide ? fast_smem_bytes<64, 32>(K) : fast_smem_bytes<64, 16>(K))
-                : D == 32 ? (wide ? fast_smem_bytes<32, 16>(K) : fast_smem_bytes<32, 8>(K))
-                          : (wide ? fast_smem_bytes<16, 8>(K) : fast_smem_bytes<16, 4>(K));
-    const int minb = D == 64 ? 1 : 2;
-    if (smem * minb > 220 * 1024) return -100;
+    if (De == 0 || work_bytes < need) return -100;
+    const size_t smem = De == 64 ? fast_smem_bytes<64, 16>(K) : De == 32 ? fast_smem_bytes<32, 8>(K) : fast_smem_bytes<16, 4>(K);
+    const int minb = De == 64 ? 1 : 2;
+    if (smem * minb > 220 * 1024) return -100;      // very large K: the per-point score table no longer fits
     float* recs = static_cast<float*>(work);
-    if (D == 64 && engine2d_enabled() && fast2d_smem_bytes(K) <= 220 * 1024 && tma_enabled()) {
-        // 2-D cyclic engine (local_step_fast2d.cuh); its record is smaller than the row-owned one, same workspace
-        launch_pack_fast2d_records(K, phi_rec, theta_rec, recs, st);
-        if (int e = launch_status()) return e;
-        FastParams p2{N, K, S, den_mode, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
-        return launch_fast2d_64(p2, st);
-    }
-    launch_pack_fast_records(K, D, phi_rec, theta_rec, recs, st);
+    launch_pack_fast_records(K, D, De, phi_rec, theta_rec, recs, st);
     if (int e = launch_status()) return e;
-    FastParams p{N, K, S, den_mode, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
-    const bool tma = tma_enabled();
-    if (D == 64) return wide ? launch_fast<64, 32>(p, tma, st) : launch_fast<64, 16>(p, tma, st);
-    if (D == 32) return wide ? launch_fast<32, 16>(p, tma, st) : launch_fast<32, 8>(p, tma, st);
-    return wide ? launch_fast<16, 8>(p, tma, st) : launch_fast<16, 4>(p, tma, st);
+    FastParams p{N, K, S, den_mode, D, (uint64_t)n_offset * (uint64_t)K, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
+    if (De == 64) return launch_fast<64, 16>(p, st);
+    if (De == 32) return launch_fast<32, 8>(p, st);
+    return launch_fast<16, 4>(p, st);
 }
 template <typename T>
 static int try_fast_t(int64_t, int, int, int, const T*, const T*, const T*, const T*, int, const T*, const T*, uint64_t,
-                      const T*, T*, T*, int32_t*, T*, double*, void*, size_t, cudaStream_t) {
+                      int64_t, const T*, T*, T*, int32_t*, T*, double*, void*, size_t, cudaStream_t) {
     return -100;
 }
 template <>
 int try_fast_t<float>(int64_t N, int K, int D, int S, const float* a, const float* b, const float* c, const float* d,
-                      int m, const float* e, const float* f, uint64_t seed, const float* g, float* h, float* i,
-                      int32_t* z, float* j, double* acc, void* work, size_t wb, cudaStream_t st) {
-    return try_fast(N, K, D, S, a, b, c, d, m, e, f, seed, g, h, i, z, j, acc, work, wb, st);
+                      int m, const float* e, const float* f, uint64_t seed, int64_t n_offset, const float* g, float* h,
+                      float* i, int32_t* z, float* j, double* acc, void* work, size_t wb, cudaStream_t st) {
+    return try_fast(N, K, D, S, a, b, c, d, m, e, f, seed, n_offset, g, h, i, z, j, acc, work, wb, st);
 }
 
 template <typename T>
 int svae_local_step(int64_t N, int K, int D, int S, const T* eta1, const T* eta2d, const T* phi_rec,
-                    const T* theta_rec, int den_mode, const T* noise, const T* gum_u, uint64_t seed, const T* x_in,
-                    T* log_r, T* x_sample, int32_t* z, T* x_k_samples, double* elbo_acc, void* work, size_t work_bytes,
-                    void* stream) {
-    if (N < 0 || K <= 0 || S <= 0) return VMP_E_BADARG;
+                    const T* theta_rec, int den_mode, const T* noise, const T* gum_u, uint64_t seed, int64_t n_offset,
+                    const T* x_in, T* log_r, T* x_sample, int32_t* z, T* x_k_samples, double* elbo_acc, void* work,
+                    size_t work_bytes, void* stream) {
+    if (N < 0 || K <= 0 || S <= 0 || n_offset < 0) return VMP_E_BADARG;
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     if (den_mode != VMP_DEN_GAUSS && den_mode != VMP_DEN_STUDENT) return VMP_E_BADMODE;
     if (N == 0) return VMP_OK;
     if (!eta1 || !eta2d || !phi_rec || !theta_rec || !log_r || !elbo_acc) return VMP_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int rc = try_fast_t<T>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed, x_in, log_r,
-                                 x_sample, z, x_k_samples, elbo_acc, work, work_bytes, st);
+    const int rc = try_fast_t<T>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed, n_offset, x_in,
+                                 log_r, x_sample, z, x_k_samples, elbo_acc, work, work_bytes, st);
     if (rc != -100) return rc;
 #define VMP_LS(DD)                                                                                              \
     case DD:                                                                                                    \
         return launch_generic<T, DD>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed, \
-                                     x_in, log_r, x_sample, z, x_k_samples, elbo_acc, st)
+                                     n_offset, x_in, log_r, x_sample, z, x_k_samples, elbo_acc, st)
     switch (D) {
         VMP_LS(1); VMP_LS(2); VMP_LS(3); VMP_LS(4); VMP_LS(5); VMP_LS(6); VMP_LS(7); VMP_LS(8);
         default:
-            return launch_generic<T, 0>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed, x_in,
-                                        log_r, x_sample, z, x_k_samples, elbo_acc, st);
+            return launch_generic<T, 0>(N, K, D, S, eta1, eta2d, phi_rec, theta_rec, den_mode, noise, gum_u, seed,
+                                        n_offset, x_in, log_r, x_sample, z, x_k_samples, elbo_acc, st);
     }
 #undef VMP_LS
 }
 
 template <typename T>
-int fill_noise(int64_t N, int K, int D, int S, uint64_t seed, T* noise, T* u, void* stream) {
-    if (N <= 0 || K <= 0 || D <= 0 || S <= 0 || (!noise && !u)) return VMP_E_BADARG;
-    fill_noise_kernel<T><<<148 * 8, 256, 0, (cudaStream_t)stream>>>(N, K, D, S, seed, noise, u);
+int fill_noise(int64_t N, int K, int D, int S, uint64_t seed, int64_t n_offset, T* noise, T* u, void* stream) {
+    if (N <= 0 || K <= 0 || D <= 0 || S <= 0 || n_offset < 0 || (!noise && !u)) return VMP_E_BADARG;
+    fill_noise_kernel<T><<<148 * 8, 256, 0, (cudaStream_t)stream>>>(N, K, D, S, seed, n_offset, noise, u);
     return launch_status();
 }
 
@@ -309,26 +288,28 @@ size_t vmp_svae_local_step_workspace_bytes(int K, int D) {
 }
 int vmp_svae_local_step_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                             const float* phi_rec, const float* theta_rec, int den_mode, const float* noise,
-                            const float* gumbel_u, uint64_t seed, const float* x_in, float* log_r, float* x_sample,
-                            int32_t* z, float* x_k_samples, double* elbo_acc, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            const float* gumbel_u, uint64_t seed, int64_t point_offset, const float* x_in, float* log_r,
+                            float* x_sample, int32_t* z, float* x_k_samples, double* elbo_acc, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     return vmp::svae_local_step<float>(N, K, D, S, eta1, eta2_diag, phi_rec, theta_rec, den_mode, noise, gumbel_u, seed,
-                                       x_in, log_r, x_sample, z, x_k_samples, elbo_acc, workspace, workspace_bytes,
+                                       point_offset, x_in, log_r, x_sample, z, x_k_samples, elbo_acc, workspace, workspace_bytes,
                                        stream);
 }
 int vmp_svae_local_step_f64(int64_t N, int K, int D, int S, const double* eta1, const double* eta2_diag,
                             const double* phi_rec, const double* theta_rec, int den_mode, const double* noise,
-                            const double* gumbel_u, uint64_t seed, const double* x_in, double* log_r, double* x_sample,
-                            int32_t* z, double* x_k_samples, double* elbo_acc, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+                            const double* gumbel_u, uint64_t seed, int64_t point_offset, const double* x_in, double* log_r,
+                            double* x_sample, int32_t* z, double* x_k_samples, double* elbo_acc, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     return vmp::svae_local_step<double>(N, K, D, S, eta1, eta2_diag, phi_rec, theta_rec, den_mode, noise, gumbel_u,
-                                        seed, x_in, log_r, x_sample, z, x_k_samples, elbo_acc, workspace,
+                                        seed, point_offset, x_in, log_r, x_sample, z, x_k_samples, elbo_acc, workspace,
                                         workspace_bytes, stream);
 }
-int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, float* noise, float* u, void* stream) {
-    return vmp::fill_noise<float>(N, K, D, S, seed, noise, u, stream);
+int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, int64_t point_offset, float* noise, float* u,
+                       void* stream) {
+    return vmp::fill_noise<float>(N, K, D, S, seed, point_offset, noise, u, stream);
 }
-int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, double* noise, double* u, void* stream) {
-    return vmp::fill_noise<double>(N, K, D, S, seed, noise, u, stream);
+int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, int64_t point_offset, double* noise, double* u,
+                       void* stream) {
+    return vmp::fill_noise<double>(N, K, D, S, seed, point_offset, noise, u, stream);
 }
 }

@@ -1,4 +1,5 @@
-// local_step_fast.cuh — the register-resident group engine of the fused local step (fp32, D in {16, 32, 64}).
+// local_step_fast.cuh — the register-resident group engine of the fused local step (fp32; engine dimension D in
+// {16, 32, 64}; a caller dimension 9 <= Dr <= 64 runs in the next engine size with an identity block in rows Dr..D-1).
 //
 // Mapping.  BS = D/4 lanes of a warp ("group") own one (point n, component k) pair; lane gl owns rows r*BS + gl,
 // r < ROWS = 4, of the D x D system.  The lower triangle of P~ = P2_k + diag(p1_n) lives in registers
@@ -33,6 +34,8 @@ namespace vmp {
 struct FastParams {
     int64_t N;
     int K, S, den_mode;
+    int Dr;                 // caller's latent dimension (<= the engine's D; rows Dr..D-1 are an identity block)
+    uint64_t pair_offset;   // n_offset * K: global pair index of (point 0, component 0) — key of the in-kernel noise
     const float* eta1;
     const float* eta2d;
     const float* recs;      // [K][REC] packed staged records
@@ -62,11 +65,8 @@ template <int D, int BS_> struct FastGeom {
 
 template <int D, int BS> struct FastLaunch;
 template <> struct FastLaunch<64, 16> { static constexpr int WARPS = 8, MINB = 1; };
-template <> struct FastLaunch<64, 32> { static constexpr int WARPS = 12, MINB = 1; };
 template <> struct FastLaunch<32, 8> { static constexpr int WARPS = 8, MINB = 2; };
-template <> struct FastLaunch<32, 16> { static constexpr int WARPS = 8, MINB = 2; };
 template <> struct FastLaunch<16, 4> { static constexpr int WARPS = 8, MINB = 2; };
-template <> struct FastLaunch<16, 8> { static constexpr int WARPS = 8, MINB = 2; };
 
 __host__ __device__ inline int fast_rec_len(int D) { return 2 * D * (D + 4) + 2 * D + 8; }
 
@@ -78,8 +78,10 @@ inline size_t fast_smem_bytes(int K) {
 }
 
 // defined in fast_d16.cu / fast_d32.cu / fast_d64.cu (one translation unit per D so they compile in parallel)
-template <int D, int BS> int launch_fast(const FastParams& p, bool use_tma, cudaStream_t st);
-void launch_pack_fast_records(int K, int D, const float* phi_rec, const float* theta_rec, float* out, cudaStream_t st);
+template <int D, int BS> int launch_fast(const FastParams& p, cudaStream_t st);
+// (phi_rec, theta_rec) of latent dimension Dr -> staged records of the engine dimension De >= Dr
+void launch_pack_fast_records(int K, int Dr, int De, const float* phi_rec, const float* theta_rec, float* out,
+                              cudaStream_t st);
 
 #ifdef VMP_FAST_IMPL
 // ---- mbarrier / bulk-copy primitives (inline PTX) ---------------------------------------------------------------
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     float* ab = xb + D;                   // [D] a = L^-1 P2 d of the current pair
     float* ib = ab + D;                   // [D] 1 / L_jj of the current pair
     float* kst = ksm + (size_t)grp * p.K * 3;
-    const int K = p.K, S = p.S;
+    const int K = p.K, S = p.S, Dr = p.Dr;
 
     if (tid == 0) {
         cta_acc[0] = cta_acc[1] = cta_acc[2] = cta_acc[3] = 0.0;
@@ -233,9 +235,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
             const int row = r * BS + gl;
-            const float p1v = -2.f * p.eta2d[n * D + row];
+            // padded rows (row >= Dr): P~ gets an identity block there (the packed P2 carries the 1), mu1 = 0
+            const bool real = row < Dr;
+            const float p1v = real ? -2.f * p.eta2d[n * Dr + row] : 0.f;
             p1b[row] = p1v;
-            mub[row] = p.eta1[n * D + row] / p1v;
+            mub[row] = real ? p.eta1[n * Dr + row] / p1v : 0.f;
             xb[row] = 0.f;
         }
         float best = -CUDART_INF_F;
@@ -366,21 +370,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             const float score = scl[0] - 0.5f * q + 0.5f * scl[1] - hld;
 
             // ---------------- phase 3: samples, ELBO terms
-            const uint64_t pair = (uint64_t)n * K + k;
+            const uint64_t pair = (uint64_t)n * K + k;                       // index into caller buffers
+            const uint64_t gpair = pair + p.pair_offset;                      // key of the in-kernel noise stream
             float snum = 0.f, sden = 0.f;
             float x0[ROWS];
             for (int s = 0; s < S; ++s) {
                 float w[ROWS], y[ROWS], idg[ROWS];
                 if (p.noise != nullptr) {
 #pragma unroll
-                    for (int r = 0; r < ROWS; ++r) w[r] = p.noise[(pair * D + r * BS + gl) * (uint64_t)S + s];
+                    for (int r = 0; r < ROWS; ++r)
+                        w[r] = (r * BS + gl < Dr) ? p.noise[(pair * Dr + r * BS + gl) * (uint64_t)S + s] : 0.f;
                 } else {
                     __syncwarp();
                     for (int qd = gl; qd < D / 4; qd += BS)
-                        reinterpret_cast<float4*>(vec)[qd] = philox_normal4(p.seed, pair, (uint32_t)s, (uint32_t)qd);
+                        reinterpret_cast<float4*>(vec)[qd] = philox_normal4(p.seed, gpair, (uint32_t)s, (uint32_t)qd);
                     __syncwarp();
 #pragma unroll
-                    for (int r = 0; r < ROWS; ++r) w[r] = vec[r * BS + gl];
+                    for (int r = 0; r < ROWS; ++r) w[r] = (r * BS + gl < Dr) ? vec[r * BS + gl] : 0.f;
                 }
                 float e2 = 0.f;
 #pragma unroll
@@ -440,7 +446,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 }
                 if (p.x_k_samples != nullptr && active) {
 #pragma unroll
-                    for (int r = 0; r < ROWS; ++r) p.x_k_samples[((pair * S) + s) * (uint64_t)D + r * BS + gl] = x[r];
+                    for (int r = 0; r < ROWS; ++r)
+                        if (r * BS + gl < Dr) p.x_k_samples[((pair * S) + s) * (uint64_t)Dr + r * BS + gl] = x[r];
                 }
                 __syncwarp();
                 float q2 = 0.f;
@@ -463,16 +470,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 q2 = group_sum<BS>(q2);
                 snum += -0.5f * e2;
                 sden += (p.den_mode == VMP_DEN_GAUSS) ? (scl[2] - 0.5f * q2)
-                                                      : (scl[2] - 0.5f * (scl[3] + (float)D) * log1pf(q2 / scl[3]));
+                                                      : (scl[2] - 0.5f * (scl[3] + (float)Dr) * log1pf(q2 / scl[3]));
             }
             // ---------------- per-pair results
             if (gl == 0) {
                 kst[3 * k + 0] = score;
-                kst[3 * k + 1] = snum / (float)S + hld - 0.5f * (float)VMP_LOG_2PI * (float)D;
+                kst[3 * k + 1] = snum / (float)S + hld - 0.5f * (float)VMP_LOG_2PI * (float)Dr;
                 kst[3 * k + 2] = sden / (float)S;
             }
             // online Gumbel-max draw of z_n (tf.multinomial GPU algorithm): keep the running arg-max and its sample
-            const float u = p.gum_u != nullptr ? p.gum_u[pair] : philox_uniform_pair(p.seed, pair);
+            const float u = p.gum_u != nullptr ? p.gum_u[pair] : philox_uniform_pair(p.seed, gpair);
             const float cand = score + gumbel_from_uniform<float>(u);
             if (cand > best) {
                 best = cand;
@@ -502,7 +509,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             }
             if (p.x_sample != nullptr) {
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) p.x_sample[n * D + r * BS + gl] = xb[r * BS + gl];
+                for (int r = 0; r < ROWS; ++r)
+                    if (r * BS + gl < Dr) p.x_sample[n * Dr + r * BS + gl] = xb[r * BS + gl];
             }
             if (p.z != nullptr && gl == 0) p.z[n] = zbest;
         }
@@ -546,23 +554,9 @@ static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     return launch_status();
 }
 
-// prefetch depth of the column-chunk loads (tuning knob VMP_FAST_PF, only compiled in for the D=64 narrow engine)
-template <int D, int BS>
-static int launch_fast_pick(const FastParams& p, bool use_tma, cudaStream_t st) {
-    if (!use_tma) return launch_fast_t<D, BS, false, 4>(p, st);
-#ifdef VMP_FAST_PF_VARIANTS
-    const char* e = std::getenv("VMP_FAST_PF");
-    const int pf = e ? std::atoi(e) : 4;
-    if (pf == 2) return launch_fast_t<D, BS, true, 2>(p, st);
-    if (pf == 6) return launch_fast_t<D, BS, true, 6>(p, st);
-    if (pf == 8) return launch_fast_t<D, BS, true, 8>(p, st);
-#endif
-    return launch_fast_t<D, BS, true, 4>(p, st);
-}
-
-#define VMP_FAST_INSTANTIATE(DD, BB)                                                                \
-    template <> int launch_fast<DD, BB>(const FastParams& p, bool use_tma, cudaStream_t st) {      \
-        return launch_fast_pick<DD, BB>(p, use_tma, st);                                           \
+#define VMP_FAST_INSTANTIATE(DD, BB)                                                  \
+    template <> int launch_fast<DD, BB>(const FastParams& p, cudaStream_t st) {      \
+        return launch_fast_t<DD, BB, true, 4>(p, st);                                \
     }
 #endif  // VMP_FAST_IMPL
 

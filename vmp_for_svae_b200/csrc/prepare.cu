@@ -232,6 +232,47 @@ spd_inverse_kernel(int D, const T* __restrict__ in, T* __restrict__ inv, T* __re
     }
 }
 
+// Dense-natural-parameter sampling (svae.sample_x_per_comp, svae.py:95-119): one CTA per (n,k) system.
+// P = -2 eta2 = L L^T; x_s = P^-1 eta1 + L^-T eps_s = L^-T (L^-1 eta1 + eps_s); thread s handles sample s.
+template <typename T>
+__global__ void __launch_bounds__(PREP_THREADS)
+gaussian_sample_nat_kernel(int D, int S, const T* __restrict__ eta1, const T* __restrict__ eta2,
+                           const T* __restrict__ noise, T* __restrict__ x, int* __restrict__ bad) {
+    extern __shared__ double sm[];
+    const int ld = D + 1;
+    double* C = sm;                     // [D][ld]
+    double* y = C + D * ld;             // [D]  L^-1 eta1
+    double* w = y + D;                  // [PREP_THREADS][D] per-thread right-hand side
+    const size_t b = blockIdx.x;
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) C[(e / D) * ld + e % D] = -2.0 * (double)eta2[b * D * D + e];
+    __syncthreads();
+    chol_lower_block(C, D, ld);
+    if (threadIdx.x == 0) {
+        bool nonpd = false;
+        for (int i = 0; i < D; ++i) {
+            double s = (double)eta1[b * D + i];
+            for (int c = 0; c < i; ++c) s -= C[i * ld + c] * y[c];
+            y[i] = s / C[i * ld + i];
+            nonpd |= !(C[i * ld + i] > 0.0);
+        }
+        if (nonpd && bad != nullptr) atomicAdd(bad, 1);
+    }
+    __syncthreads();
+    for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+        const int s = s0 + threadIdx.x;
+        if (s < S) {
+            double* v = w + (size_t)threadIdx.x * D;
+            for (int i = 0; i < D; ++i) v[i] = y[i] + (double)noise[(b * D + i) * S + s];      // noise[N,K,D,S]
+            for (int i = D - 1; i >= 0; --i) {                                                  // L^T x = v
+                double t = v[i];
+                for (int c = i + 1; c < D; ++c) t -= C[c * ld + i] * v[c];
+                v[i] = t / C[i * ld + i];
+            }
+            for (int i = 0; i < D; ++i) x[(b * S + s) * D + i] = (T)v[i];                        // x[N,K,S,D]
+        }
+    }
+}
+
 static size_t prep_smem(int D, int nmat) { return sizeof(double) * ((size_t)nmat * D * (D + 1) + D + 64); }
 
 template <typename K>
@@ -285,10 +326,31 @@ int spd_inverse(int K, int D, const T* in, T* inv, T* logdet, void* stream) {
     return launch_status();
 }
 
+template <typename T>
+int gaussian_sample_nat(int64_t B, int D, int S, const T* eta1, const T* eta2, const T* noise, T* x, int* bad,
+                        void* stream) {
+    if (B < 0 || S <= 0) return VMP_E_BADARG;
+    if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
+    if (B == 0) return VMP_OK;
+    if (!eta1 || !eta2 || !noise || !x || B > 0x7fffffffLL) return VMP_E_BADARG;
+    const size_t sm = sizeof(double) * ((size_t)D * (D + 1) + D + (size_t)PREP_THREADS * D);
+    if (int e = set_smem(gaussian_sample_nat_kernel<T>, sm)) return e;
+    gaussian_sample_nat_kernel<T><<<(unsigned)B, PREP_THREADS, sm, (cudaStream_t)stream>>>(D, S, eta1, eta2, noise, x, bad);
+    return launch_status();
+}
+
 }  // namespace vmp
 
 extern "C" {
-int vmp_version(void) { return 100; }
+int vmp_version(void) { return 200; }
+int vmp_gaussian_sample_nat_f32(int64_t B, int D, int S, const float* eta1, const float* eta2, const float* noise,
+                                float* x, int* non_pd, void* s) {
+    return vmp::gaussian_sample_nat<float>(B, D, S, eta1, eta2, noise, x, non_pd, s);
+}
+int vmp_gaussian_sample_nat_f64(int64_t B, int D, int S, const double* eta1, const double* eta2, const double* noise,
+                                double* x, int* non_pd, void* s) {
+    return vmp::gaussian_sample_nat<double>(B, D, S, eta1, eta2, noise, x, non_pd, s);
+}
 int vmp_phi_record_len(int D) { return vmp::phi_record_len(D); }
 int vmp_theta_record_len(int D) { return vmp::theta_record_len(D); }
 int vmp_stats_len(int D) { return vmp::stats_len(D); }

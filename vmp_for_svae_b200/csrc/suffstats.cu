@@ -10,7 +10,6 @@
 // atomicAdd per output per CTA.
 #include "common.cuh"
 
-#include <cstdlib>
 
 namespace vmp {
 
@@ -294,7 +293,7 @@ static int launch_suffstats_small(int64_t N, int K, const T* x, const T* r, int 
     return launch_status();
 }
 
-// tensor-core contraction (suffstats_tc.cu): fp32, D = 64, even K, GMM weights; VMP_SUFFSTATS_TC=0 disables it
+// tensor-core contraction (suffstats_tc.cu): fp32, D = 64, even K, GMM weights, N >= 128
 int suffstats_tc(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, double* stats, cudaStream_t st);
 template <typename T>
 static int suffstats_tc_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, cudaStream_t) { return -100; }
@@ -302,8 +301,6 @@ template <>
 int suffstats_tc_dispatch<float>(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
                                  double* stats, cudaStream_t st) {
     if (u_nk != nullptr) return -100;
-    const char* e = std::getenv("VMP_SUFFSTATS_TC");
-    if (e && e[0] == '0') return -100;
     return suffstats_tc(N, K, D, x, r, r_is_log, stats, st);
 }
 

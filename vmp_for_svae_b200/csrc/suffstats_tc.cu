@@ -24,7 +24,6 @@
 
 namespace vmp {
 
-__device__ int g_suffstats_tc_status = 0;      // set to 1 if an mbarrier wait ever ran out of its spin budget
 
 constexpr int TC_D = 64, TC_PC = 32, TC_THREADS = 256, TC_FLUSH = 16;
 constexpr int TC_ITEMS = (TC_D * TC_PC / 4) / TC_THREADS;      // (feature, point-quad) items per builder thread
@@ -253,7 +252,9 @@ suffstats_tc_kernel(int64_t N, int K, int64_t pts_per_slice, const float* __rest
             lastbuf = buf;
             if ((it + 1) % TC_FLUSH == 0 || it + 1 == nchunks) drain(lastbuf);
         }
-        if (!ok && tid == 0) atomicExch(&g_suffstats_tc_status, 1);
+        // an mbarrier wait that exhausted its spin budget means the tensor pipe never signalled: the accumulator is
+        // incomplete — abort the launch (sticky CUDA error at the caller) rather than add wrong statistics
+        if (!ok) __trap();
 
         // fp64 partials of this CTA -> global statistics (lower triangle mirrored: exactly symmetric)
         const int SL = stats_len(TC_D);

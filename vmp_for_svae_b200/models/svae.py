@@ -96,12 +96,31 @@ def unpack_smm(theta_smm, name='unpack_theta_smm'):
     return mu, rec[:, :D * D].reshape(K, D, D).clone()
 
 
-def e_step(phi_enc, phi_gmm, nb_samples, seed=0, name="e_step", *, noise=None, u=None, materialize=True):
+class NonPDFlag(object):
+    """Device-side count of non-positive Cholesky pivots of an e_step call (the TF graph raises InvalidArgumentError
+    for these at sess.run time).  Reading it is the only host synchronisation: `e_step` itself never syncs, so the
+    surface can be captured in a CUDA graph; `raise_if_set()` (or e_step(..., check=True)) reproduces the raise."""
+
+    def __init__(self, acc):
+        self.acc = acc
+
+    def count(self):
+        return float(self.acc[3])
+
+    def raise_if_set(self):
+        if self.count() != 0.0:
+            raise RuntimeError('Cholesky decomposition was not successful. The input might not be valid.')
+
+
+def e_step(phi_enc, phi_gmm, nb_samples, seed=0, name="e_step", *, noise=None, u=None, materialize=True, check=False):
     """svae.py:14-47.
 
     Returns (x_k_samples[N,K,S,D], log_z_given_y_phi[N,K], phi_tilde, dbg).  `phi_tilde` and `dbg` are lazy
     (unpacking them materialises the [N,K,D,D] tensors); with materialize=False x_k_samples is None.
-    noise: eps[N,K,D,S] (the raw_noise of svae.py:113-114); default: in-kernel Philox keyed by `seed`."""
+    noise: eps[N,K,D,S] (the raw_noise of svae.py:113-114); default: in-kernel Philox keyed by `seed`.
+    u: Gumbel uniforms [N,K] of the fused categorical draw (only used by the training graph's forward).
+    No host synchronisation: a non-PD system is reported through `phi_tilde.non_pd` (NonPDFlag); check=True reads it
+    here and raises like the reference's sess.run does."""
     eta1_phi1, eta2_phi1_diag = phi_enc
     N, D = eta1_phi1.shape
     assert tuple(eta2_phi1_diag.shape) == (N, D)
@@ -123,10 +142,11 @@ def e_step(phi_enc, phi_gmm, nb_samples, seed=0, name="e_step", *, noise=None, u
         out = core.local_step(eta1_phi1, eta2_phi1_diag, phi_rec, _zero_theta_rec(K, D, eta1_phi1), int(nb_samples),
                               noise=noise, u=u, seed=seed, want_x_sample=False, want_z=False,
                               materialize_x_k=bool(materialize))
-    if float(out['elbo_acc'][3]) != 0.0:
-        raise RuntimeError('Cholesky decomposition was not successful. The input might not be valid.')
     eta2_phi2 = -0.5 * phi_rec[:, :D * D].reshape(K, D, D)
     phi_tilde = PhiTilde((eta1_phi1.detach(), eta2_phi1_diag.detach()), eta1_phi2.detach(), eta2_phi2, phi_rec)
+    phi_tilde.non_pd = NonPDFlag(out['elbo_acc'])
+    if check:
+        phi_tilde.non_pd.raise_if_set()
     phi_tilde.seed, phi_tilde.noise = seed, noise
     # autograd bookkeeping: compute_elbo re-enters the fused step with theta to get a differentiable regulariser
     phi_tilde.leaves, phi_tilde.x_k, phi_tilde.S = leaves, out['x_k_samples'], int(nb_samples)
@@ -161,25 +181,31 @@ def compute_log_z_given_y(eta1_phi1, eta2_phi1, eta1_phi2, eta2_phi2, pi_phi2, n
 
 def sample_x_per_comp(eta1, eta2, nb_samples, seed=0, *, noise=None):
     """svae.py:95-119 for dense eta1[N,K,D,1], eta2[N,K,D,D] (general API form; the fused path never builds these):
-    x = P^-1 eta1 + L^-T eps, L = chol(P), P = -2 eta2 -> [N,K,S,D]."""
+    x = P^-1 eta1 + L^-T eps, L = chol(P), P = -2 eta2 -> [N,K,S,D]  (vmp_gaussian_sample_nat, csrc/prepare.cu)."""
     N, K, _, D = eta2.shape
-    P = -2.0 * eta2
     if noise is None:
         noise, _ = core.fill_noise(N, K, D, int(nb_samples), seed, eta2.dtype, eta2.device, want_u=False)
-    Lc = torch.linalg.cholesky(P)
-    nz = torch.linalg.solve_triangular(Lc.transpose(-1, -2), noise, upper=True)
-    mean = torch.cholesky_solve(eta1, Lc)
-    return (mean + nz).permute(0, 1, 3, 2).contiguous()
+    x, _ = core.gaussian_sample_nat(eta1, eta2.contiguous(), noise)
+    return x
 
 
-def subsample_x(x_k_samples, log_q_z_given_y, seed=0, *, u=None, gumbel_u=None):
+def subsample_x(x_k_samples, log_q_z_given_y, seed=0, *, cdf_u=None, gumbel_u=None, u=None):
     """svae.py:122-151 : x_samples[n,s] = x_k_samples[n, z_ns, s], z_ns ~ Cat(softmax(log q)) (tf.multinomial).
-    Default / gumbel_u[N,S,K]: Gumbel-max, z = argmax_k(log q - log(-log u)) (TF's GPU kernel; for s = 0 and the same
-    `seed` this is the draw the fused step makes).  u[N,S]: inverse-CDF search in double (TF's CPU kernel).
-    Stand-alone form of the gather for the reference's call order; the fused step selects inside the kernel."""
+    Default / gumbel_u[N,S,K] (or [N,K] for S = 1): Gumbel-max, z = argmax_k(log q - log(-log u)) (TF's GPU kernel; for
+    s = 0 and the same `seed` this is the draw the fused step makes).  cdf_u[N,S]: inverse-CDF search in double (TF's CPU
+    kernel).  `u=` is the old name of cdf_u.  Stand-alone form of the gather for the reference's call order; the fused
+    step selects inside the kernel."""
     N, K, S, L = x_k_samples.shape
     dev = x_k_samples.device
+    if cdf_u is None:
+        cdf_u = u
+    if gumbel_u is not None and gumbel_u.dim() == 2:
+        assert tuple(gumbel_u.shape) == (N, K) and S == 1, 'gumbel_u[N,K] needs one sample per component'
+        gumbel_u = gumbel_u.unsqueeze(1)
+    u = cdf_u
     if u is not None:
+        assert tuple(u.shape) == (N, S), 'cdf_u must be [N,S] (inverse-CDF uniforms); Gumbel uniforms go in gumbel_u'
+
         lg = log_q_z_given_y.to(torch.float64)
         cdf = torch.cumsum(torch.exp(lg - lg.max(dim=1, keepdim=True).values), dim=1)
         z = torch.searchsorted(cdf, u.to(torch.float64) * cdf[:, -1:], right=True).clamp_(max=K - 1)
@@ -313,14 +339,16 @@ def predict(y, phi_gmm, encoder, decoder, seed=0):
 
 
 def inference(y, phi_gmm, encoder, decoder, nb_samples=10, stddev_init_nn=0.01, seed=0, name='inference',
-              param_device=None, *, noise=None, u=None):
+              param_device=None, *, noise=None, cdf_u=None, gumbel_u=None, u=None):
     """svae.py:499-516 -> (y_reconstruction, x_given_y_phi, x_k_samples, x_samples, log_z_given_y_phi, phi_gmm,
-    phi_tilde).  encoder / decoder are torch callables (the reference builds them from layer specs)."""
+    phi_tilde).  encoder / decoder are torch callables (the reference builds them from layer specs).
+    The categorical draw of subsample_x: gumbel_u[N,S,K] (Gumbel-max) or cdf_u[N,S] (inverse CDF; `u=` is its old name)."""
     x_given_y_phi = encoder(y)
     x_given_y_phi = (x_given_y_phi[0].contiguous(), x_given_y_phi[1].contiguous())
     x_k_samples, log_z_given_y_phi, phi_tilde, _ = e_step(x_given_y_phi, phi_gmm, nb_samples, seed=seed, noise=noise)
     y_reconstruction = decoder(x_k_samples)
-    x_samples = subsample_x(x_k_samples, log_z_given_y_phi, seed, u=u)[:, 0, :]
+    x_samples = subsample_x(x_k_samples, log_z_given_y_phi, seed, cdf_u=cdf_u if cdf_u is not None else u,
+                            gumbel_u=gumbel_u)[:, 0, :]
     return y_reconstruction, x_given_y_phi, x_k_samples, x_samples, log_z_given_y_phi, phi_gmm, phi_tilde
 
 

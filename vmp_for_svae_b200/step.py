@@ -17,8 +17,12 @@ from . import core, _lib
 
 class SVAEStep(object):
     def __init__(self, N_local, K, D, S=1, dtype=torch.float32, device='cuda', den_mode=core.DEN_GAUSS,
-                 process_group=None, use_dist=None):
+                 process_group=None, use_dist=None, point_offset=0):
+        """point_offset: global index of this rank's first point (dist.shard_range(...)[0]).  The in-kernel noise is
+        keyed by the global pair index, so the sharded step draws exactly what the single-GPU step over the whole
+        batch draws (every rank passes the same `seed`)."""
         self.N, self.K, self.D, self.S = int(N_local), int(K), int(D), int(S)
+        self.point_offset = int(point_offset)
         self.dtype, self.device, self.den_mode = dtype, torch.device(device), den_mode
         plen, tlen, slen = _lib.record_lens(D)
         e = lambda *s, dt=dtype: torch.empty(*s, dtype=dt, device=self.device)
@@ -52,7 +56,7 @@ class SVAEStep(object):
             kernel_events[0].record()
         core.local_step(eta1, eta2_diag, self.phi_rec, self.theta_rec, self.S, den_mode=self.den_mode, noise=noise,
                         u=u, seed=seed, log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc,
-                        workspace=self.workspace)
+                        workspace=self.workspace, point_offset=self.point_offset)
         if kernel_events is not None:
             kernel_events[1].record()
         core.suffstats(self.x_sample, self.log_r, r_is_log=True, stats=self.stats)
@@ -107,9 +111,8 @@ def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, st
     chunk=None: one copy, then `stepper.step`.  chunk=C (points): the shard is processed in chunks of C points with the
     host->device copy of chunk c+1 (own stream, two staging slots) overlapping the local step + statistics of chunk c;
     the statistics and ELBO terms accumulate on the device and the all-reduce / natural-gradient update run once at
-    the end, so the result is the same VMP step.  The in-kernel noise stream is keyed per chunk (seed mixed with the
-    chunk index), i.e. a different but equally valid draw than the unchunked call; with injected `noise` / `u` the two
-    are identical (tests)."""
+    the end, so the result is the same VMP step: the in-kernel noise stream is keyed by the global pair index
+    (point_offset of each chunk), so chunked, unchunked and sharded calls make the same draws (tests)."""
     eta1_h, eta2_h = phi_enc_host
     N = eta1_h.shape[0]
     st = stepper
@@ -148,7 +151,7 @@ def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, st
             cur.wait_event(ready[slot])
             core.local_step(slots[slot][0][:m], slots[slot][1][:m], st.phi_rec, st.theta_rec, st.S, den_mode=st.den_mode,
                             noise=None if noise is None else noise[lo:hi], u=None if u is None else u[lo:hi],
-                            seed=(int(seed) * 0x9E3779B97F4A7C15 + c) & 0xFFFFFFFFFFFFFFFF, log_r=st.log_r[lo:hi],
+                            seed=seed, point_offset=st.point_offset + lo, log_r=st.log_r[lo:hi],
                             x_sample=st.x_sample[lo:hi], z=st.z[lo:hi], elbo_acc=st.elbo_acc, workspace=st.workspace)
             free[slot].record(cur)
             core.suffstats(st.x_sample[lo:hi], st.log_r[lo:hi], r_is_log=True, stats=st.stats)
