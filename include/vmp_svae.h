@@ -191,6 +191,45 @@ int vmp_mixture_estep_f64(int64_t N, int K, int D, const double* x, const double
                           const uint8_t* missing_mask, double* r, double* u_out, double* pi, double* work,
                           void* stream);
 
+/* Whole VB-EM sweeps: n_sweeps x [ m_step(r[,u]) -> P = inv(C) -> e_step -> (r[,u]) ], i.e. gmm.inference (gmm.py:230-269) /
+ * smm.inference (smm.py:199-245) applied n_sweeps times to the state (the reference's driver loops gmm.py:377-379 and
+ * smm.py __main__).  In: x[N,D]; the prior in standard parameters alpha_0[K], beta_0[K], m_0[K,D], C_0[K,D,D], v_0[K]
+ * (niw.natural_to_standard / dirichlet.natural_to_standard of init_mm_params, gmm.py:246-252); kappa_k[K] (SMM, is_smm != 0);
+ * state r[N,K] (and u[N,K] for the SMM), read as the input of the first M-step and overwritten with the state after the last
+ * sweep.  Out (of the LAST sweep's M-step): alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi = exp(E log pi).
+ * fp32 with D <= 8 and K <= 32 runs the fused kernels of mixture_sweep.cu (inside a multi-sweep call r and u stay on chip:
+ * the e-step accumulates the next M-step's statistics; only the last sweep writes the state); other shapes run the general
+ * kernels sweep by sweep.  workspace: vmp_mixture_fit_workspace_bytes(K, D) bytes of device scratch.                   */
+size_t vmp_mixture_fit_workspace_bytes(int K, int D);
+/* The phases of one sweep as separate calls (a multi-rank sweep all-reduces the statistics between them; vmp_mixture_fit is
+ * their single-process composition):
+ *   vmp_suffstats_*            statistics of the state (r[,u])
+ *   vmp_mixture_prepare_*      K-sized: M-step in standard parameters from the (all-reduced) statistics + P_k = C_k^-1 + the
+ *                              e-step constants; optional outputs P_k[K,D,D], cst[K] (inputs of vmp_mixture_estep_*) and
+ *                              rec[K, vmp_mixture_record_len(D)] (input of vmp_mixture_estep_fused_f32; D <= 8);
+ *                              stats_next (may be NULL) is zeroed for the next accumulation
+ *   vmp_mixture_estep_fused_f32   fp32, D <= 8, K <= 32: e-step from the packed records; writes r[,u] when write_state != 0
+ *                              and / or accumulates the statistics of the NEW state into stats_next (non-NULL)            */
+int vmp_mixture_record_len(int D);
+int vmp_mixture_prepare_f32(int K, int D, int is_smm, const double* stats, double* stats_next, const float* alpha_0,
+                            const float* beta_0, const float* m_0, const float* C_0, const float* v_0, const float* kappa_k,
+                            float* alpha_k, float* beta_k, float* m_k, float* C_k, float* v_k, float* x_k, float* S_k, float* pi,
+                            float* P_k, float* cst, float* rec, void* stream);
+int vmp_mixture_prepare_f64(int K, int D, int is_smm, const double* stats, double* stats_next, const double* alpha_0,
+                            const double* beta_0, const double* m_0, const double* C_0, const double* v_0, const double* kappa_k,
+                            double* alpha_k, double* beta_k, double* m_k, double* C_k, double* v_k, double* x_k, double* S_k,
+                            double* pi, double* P_k, double* cst, float* rec, void* stream);
+int vmp_mixture_estep_fused_f32(int64_t N, int K, int D, int is_smm, const float* x, const float* rec, float* r, float* u,
+                                double* stats_next, int write_state, void* stream);
+int vmp_mixture_fit_f32(int64_t N, int K, int D, int is_smm, int n_sweeps, const float* x, const float* alpha_0,
+                        const float* beta_0, const float* m_0, const float* C_0, const float* v_0, const float* kappa_k, float* r,
+                        float* u, float* alpha_k, float* beta_k, float* m_k, float* C_k, float* v_k, float* x_k, float* S_k,
+                        float* pi, void* workspace, size_t workspace_bytes, void* stream);
+int vmp_mixture_fit_f64(int64_t N, int K, int D, int is_smm, int n_sweeps, const double* x, const double* alpha_0,
+                        const double* beta_0, const double* m_0, const double* C_0, const double* v_0, const double* kappa_k,
+                        double* r, double* u, double* alpha_k, double* beta_k, double* m_k, double* C_k, double* v_k, double* x_k,
+                        double* S_k, double* pi, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Batched SPD inverse + log-determinant of K matrices (tf.matrix_inverse at gmm.py:260 / smm.py:234,
  * helpers/tf_utils.logdet 25-49).  in[K,D,D] -> inv[K,D,D] (may be NULL), logdet[K] (may be NULL).      */
 int vmp_spd_inverse_f32(int K, int D, const float* in, float* inv, float* logdet, void* stream);

@@ -35,6 +35,16 @@ def relerr(a, b, floor):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))) if a.size else 0.0
 
 
+def check_abs(name, a, b, atol, **ctx):
+    """absolute error (check() with a floor turns relative as soon as |ref| exceeds the floor)"""
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, dtype=np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape and np.all(np.isfinite(a))
+    e = float(np.max(np.abs(a - b))) if a.size else 0.0
+    _report(quantity=name, err=e, atol=atol, **ctx)
+    assert e <= atol, '%s: max abs err %.3e > %.1e (%s)' % (name, e, atol, ctx)
+
+
 def check(name, a, b, rtol, floor, **ctx):
     e = relerr(a, b, floor)
     _report(quantity=name, err=e, rtol=rtol, floor=floor, **ctx)
@@ -54,10 +64,11 @@ def rtol_for(dt, D, base=None):
 def logr_atol(dt, D):
     """absolute tolerance on the raw log-responsibility (every k with r > 1e-12).  fp32: the score is a sum of O(D)
     terms of magnitude O(10..100); LAPACK fp32 on the same centred formulation reaches 5e-6..7e-6 on these inputs
-    (tools/fp32_floor.py), the kernels (MUFU rsqrt+Newton, MUFU lg2) are allowed 3x that."""
+    (measured: profiles/r2_parity_nondegenerate.md), the kernels (MUFU rsqrt + Newton step, MUFU lg2) measure 1e-6 (D=8),
+    4e-6 (D=16), 8e-6 (D=32), 2e-5 (D=64, K=128) on the same inputs; the bound leaves 2-3x headroom."""
     if dt == torch.float64:
         return 1e-9
-    return 2e-5
+    return 2e-5 if D <= 16 else (3e-5 if D <= 32 else 5e-5)
 
 
 def golden_inputs(g, dt):
@@ -90,7 +101,7 @@ def test_svae_surface_vs_reference_golden(case, dt):
         r_gold = np.exp(g['log_r'])
         assert (r_gold.max(1) < 0.99).mean() >= 0.8, 'golden case is degenerate'
         m = torch.as_tensor(g['log_r'] > np.log(1e-12), device=DEV)
-        check('raw log_r (abs, r > 1e-12)', log_r[m], g['log_r'][m.cpu().numpy()], logr_atol(dt, D), 1.0, **ctx)
+        check_abs('raw log_r (abs, r > 1e-12)', log_r[m], g['log_r'][m.cpu().numpy()], logr_atol(dt, D), **ctx)
     if 'x_k' in g:
         check('x_k_samples', x_k, g['x_k'], rt, 1.0, **ctx)
         e1, e2 = phi_tilde
@@ -217,8 +228,8 @@ def test_nondegenerate_step_vs_oracle(cfg, dt):
     lr = out['log_r'].double().cpu()
     m = r_ref > 1e-12
     assert int(m.sum()) > 0.5 * N * K
-    check('nondegenerate raw log_r (abs)', lr[m], ref['log_r'][m], logr_atol(dt, D), 1.0, **ctx)
-    check('nondegenerate r_nk', torch.exp(lr), r_ref, TOL[dt] * (1 if dt == torch.float64 else 2), 1e-3, **ctx)
+    check_abs('nondegenerate raw log_r (abs)', lr[m], ref['log_r'][m], logr_atol(dt, D), **ctx)
+    check('nondegenerate r_nk', torch.exp(lr), r_ref, logr_atol(dt, D), 1e-3, **ctx)
     zc = out['z'].cpu().long()
     agree = (zc == ref['z']).double().mean().item()
     assert agree >= (1.0 if dt == torch.float64 else 0.97), 'z agreement %.4f' % agree
@@ -270,10 +281,10 @@ def test_c3_sweep_vs_oracle(kappa, dt):
         md = mixtures.expct_mahalanobis_dist(xt, th_ref[1], th_ref[2], torch.linalg.inv(th_ref[3]), th_ref[4])
         score_mag = float((0.5 * (D + kappa) * md)[m].max())
         atol = 1e-9 * max(1.0, score_mag / 100) if dt == torch.float64 else 32 * 6e-8 * score_mag * mult
-        rr = rt * mult if kappa < 100 else max(rt * mult, 2 * atol)          # r inherits the score's absolute error
+        rr = max(rt * mult, 2 * atol)                                        # r inherits the score's absolute error
         check('c3 r', r_g, r_ref, rr, 1e-3, **ctx)
         check('c3 u', u_g, u_ref, rt * mult, 1e-3, **ctx)
-        check('c3 raw log r (abs)', log_r_g.double().cpu()[m], torch.log(r_ref)[m], atol, 1.0, score_mag=score_mag, **ctx)
+        check_abs('c3 raw log r (abs)', log_r_g.double().cpu()[m], torch.log(r_ref)[m], atol, score_mag=score_mag, **ctx)
         for a, b_, n in zip(th_g[:5], th_ref[:5], ['alpha_k', 'beta_k', 'm_k', 'C_k', 'v_k']):
             check('c3 ' + n, a, b_, rt * mult, float(b_.abs().max()), **ctx)
         check('c3 pi', pi_g, pi_ref, rt * mult, 1e-3, **ctx)
@@ -417,6 +428,65 @@ def test_smm_sweep_vs_reference_golden(case, dt):
 
 
 @pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('model', ['gmm', 'smm'])
+@pytest.mark.parametrize('shape', [(3000, 12, 5), (2049, 32, 8), (700, 40, 3), (500, 6, 12)], ids=lambda s: 'N%dK%dD%d' % s)
+def test_fit_equals_repeated_inference(shape, model, dt):
+    """gmm.fit / smm.fit (the reference's driver loop in one call; fp32 D<=8 K<=32: r, u stay on chip between sweeps) ==
+    the same number of single-sweep inference calls on the same state; (700,40,3) and (500,6,12) take the general kernels."""
+    from vmp_for_svae_b200.models import gmm, smm
+    N, K, D = shape
+    rs = np.random.RandomState(N)
+    cen = 2.0 * rs.randn(5, D)
+    x = T(cen[rs.randint(0, 5, N)] + rs.randn(N, D), dt, DEV)
+    r0 = T(rs.dirichlet(np.ones(K), N), dt, DEV)
+    sweeps = 4
+    ra, ua = r0.clone(), torch.ones_like(r0)
+    rb, ub = r0.clone(), torch.ones_like(r0)
+    for _ in range(sweeps):
+        outa = smm.inference(x, K, 5.0, 0, r_nk=ra, u_nk=ua) if model == 'smm' else gmm.inference(x, K, 0, r_nk=ra)
+    outb = smm.fit(x, K, 5.0, 0, sweeps, r_nk=rb, u_nk=ub) if model == 'smm' else gmm.fit(x, K, 0, sweeps, r_nk=rb)
+    torch.cuda.synchronize()
+    rt = 1e-9 if dt == torch.float64 else 3e-4       # fp32: rounding differences of sweep 1 are amplified by 3 more sweeps
+    ctx = dict(shape=list(shape), model=model, dtype=str(dt))
+    check('fit r', rb, ra, rt, 1e-3, **ctx)
+    if model == 'smm':
+        check('fit u', ub, ua, rt, 1e-3, **ctx)
+    for a, b in zip(outb[2][:5], outa[2][:5]):
+        check('fit theta', a, b, rt, float(b.abs().max()), **ctx)
+    for a, b in zip(outb[3], outa[3]):
+        check('fit moments', a, b, rt, max(float(b.abs().max()), 1e-3), **ctx)
+    assert abs(float(rb.sum()) - N) < 1e-3 * N
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+def test_sharded_mixture_sweep_equals_fit(dt):
+    """mixture_step.MixtureSweep (the phases of a sweep as separate calls, all-reduce in between when distributed) == smm.fit;
+    and two shards whose statistics are summed by hand == the full batch (what two ranks compute)."""
+    from vmp_for_svae_b200 import core
+    from vmp_for_svae_b200.mixture_step import MixtureSweep
+    from vmp_for_svae_b200.models import smm
+    N, K, D = 5000, 32, 8
+    rs = np.random.RandomState(3)
+    x = T(2.0 * rs.randn(6, D)[rs.randint(0, 6, N)] + rs.randn(N, D), dt, DEV)
+    r0 = T(rs.dirichlet(np.ones(K), N), dt, DEV)
+    prior = smm._prior_standard(K, D, 0, dt, torch.device(DEV))
+    kap = torch.full((K,), 5.0, dtype=dt, device=DEV)
+    ra, ua = r0.clone(), torch.ones_like(r0)
+    oa = smm.fit(x, K, 5.0, 0, 3, r_nk=ra, u_nk=ua)
+    rb, ub = r0.clone(), torch.ones_like(r0)
+    ob = MixtureSweep(K, D, prior, kappa_k=kap, dtype=dt, device=DEV, use_dist=False).fit(x, rb, ub, 3)
+    rt = 1e-9 if dt == torch.float64 else 2e-4
+    check('sweep class r', rb, ra, rt, 1e-3); check('sweep class u', ub, ua, rt, 1e-3)
+    check('sweep class C_k', ob['C_k'], oa[2][3], rt, float(oa[2][3].abs().max()))
+    # two shards: statistics add
+    cut = N // 3
+    full = core.suffstats(x, r0, u_nk=torch.ones_like(r0))
+    parts = core.suffstats(x[:cut].contiguous(), r0[:cut].contiguous(), u_nk=torch.ones_like(r0[:cut])) + \
+        core.suffstats(x[cut:].contiguous(), r0[cut:].contiguous(), u_nk=torch.ones_like(r0[cut:]))
+    torch.testing.assert_close(parts, full, rtol=1e-6 if dt == torch.float32 else 1e-12, atol=1e-6)
+
+
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
 def test_distributions_vs_reference_golden(dt):
     from vmp_for_svae_b200.distributions import dirichlet, gaussian, niw, student_t
     g = load_golden('distributions')
@@ -553,9 +623,10 @@ def test_chunked_host_step_equals_unchunked():
     for chunk in (None, 256):
         st = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False)
         th = dev(theta)
-        elbo, alpha = svae_step_host(host, dev(phi_gmm), th, dev(prior), 0.3, st, chunk=chunk, noise=nz, u=uu)
+        elbo, theta_h = svae_step_host(host, dev(phi_gmm), th, dev(prior), 0.3, st, chunk=chunk, noise=nz, u=uu)
         torch.cuda.synchronize()
-        res.append((elbo, alpha, st.log_r.clone(), st.z.clone(), st.x_sample.clone(), [t.clone() for t in th]))
+        assert len(theta_h) == 5 and all(torch.equal(h, t.cpu()) for h, t in zip(theta_h, th))   # all of theta comes back
+        res.append((elbo, theta_h[0].numpy(), st.log_r.clone(), st.z.clone(), st.x_sample.clone(), [t.clone() for t in th]))
     a, b = res
     assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
     assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-9) and np.allclose(a[1], b[1], rtol=1e-6)

@@ -28,6 +28,8 @@ _SIGS_T = {
     'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_ptr, c_int] + [c_ptr] * 15 + [c_ptr],
     'vmp_mixture_mstep': [c_int, c_int, c_int, c_ptr] + [c_ptr] * 12 + [c_ptr],
     'vmp_mixture_estep': [c_i64, c_int, c_int] + [c_ptr] * 12 + [c_ptr],
+    'vmp_mixture_fit': [c_i64, c_int, c_int, c_int, c_int] + [c_ptr] * 17 + [c_ptr, ctypes.c_size_t, c_ptr],
+    'vmp_mixture_prepare': [c_int, c_int, c_int, c_ptr, c_ptr] + [c_ptr] * 17 + [c_ptr],
     'vmp_spd_inverse': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_decoder_loglike': [c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_decoder_loglike_bwd': [c_i64, c_int, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_ptr,
@@ -43,9 +45,12 @@ _SIGS = {
     'vmp_stats_len': [c_int],
     'vmp_svae_local_step_workspace_bytes': [c_int, c_int],
     'vmp_svae_local_step_bwd_workspace_bytes': [c_int, c_int],
+    'vmp_mixture_fit_workspace_bytes': [c_int, c_int],
+    'vmp_mixture_record_len': [c_int],
+    'vmp_mixture_estep_fused_f32': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
     'vmp_fma_probe': [c_int, c_int, c_int, c_ptr, c_ptr],
 }
-EXPORTS = sorted(list(_SIGS) + [n + s for n in _SIGS_T for s in ('_f32', '_f64')])
+EXPORTS = sorted([n for n in _SIGS] + [n + s for n in _SIGS_T for s in ('_f32', '_f64')])
 
 
 class VmpError(RuntimeError):

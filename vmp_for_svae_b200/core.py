@@ -199,7 +199,7 @@ def mixture_mstep(stats, D, is_smm, alpha_0, beta_0, m_0, C_0, v_0):
     return out
 
 
-def mixture_estep(x, alpha_k, beta_k, m_k, P_k, v_k, kappa_k=None, missing_mask=None, r=None, u_out=None):
+def mixture_estep(x, alpha_k, beta_k, m_k, P_k, v_k, kappa_k=None, missing_mask=None, r=None, u_out=None, work=None):
     N, D = x.shape
     K = alpha_k.shape[0]
     dt, dev = x.dtype, x.device
@@ -213,7 +213,7 @@ def mixture_estep(x, alpha_k, beta_k, m_k, P_k, v_k, kappa_k=None, missing_mask=
     if kappa_k is not None and u_out is None:
         u_out = torch.empty(N, K, dtype=dt, device=dev)
     pi = torch.empty(K, dtype=dt, device=dev)
-    work = torch.empty(K, dtype=dt, device=dev)
+    work = work if work is not None else torch.empty(K, dtype=dt, device=dev)
     _lib.call('vmp_mixture_estep', dt, N, K, D, ptr(x), ptr(alpha_k), ptr(beta_k), ptr(m_k), ptr(P_k), ptr(v_k),
               ptr(kappa_k), ptr(missing_mask), ptr(r), ptr(u_out), ptr(pi), ptr(work), stream_ptr(dev), device=dev)
     return r, u_out, pi
@@ -310,3 +310,69 @@ def gaussian_sample_nat(eta1, eta2, noise):
     _lib.call('vmp_gaussian_sample_nat', dt, N * K, D, S, ptr(eta1), ptr(eta2), ptr(noise), ptr(x), ptr(bad),
               stream_ptr(dev), device=dev)
     return x, bad
+
+
+def mixture_fit(x, r, u, prior_std, kappa_k=None, n_sweeps=1):
+    """n_sweeps VB-EM sweeps of gmm.inference / smm.inference on the state (r[, u]) IN PLACE (vmp_mixture_fit).
+    prior_std = (alpha_0, beta_0, m_0, C_0, v_0) in standard parameters.  Returns the last M-step's
+    (alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi)."""
+    N, D = x.shape
+    K = r.shape[1]
+    dt, dev = x.dtype, x.device
+    x = _chk(x, (N, D), dt, 'x')
+    assert r.is_contiguous() and tuple(r.shape) == (N, K) and r.dtype == dt, 'r_nk must be a contiguous [N,K] state tensor'
+    is_smm = kappa_k is not None
+    if is_smm:
+        assert u is not None and u.is_contiguous() and tuple(u.shape) == (N, K) and u.dtype == dt, 'u_nk state'
+        kappa_k = _chk(kappa_k, (K,), dt, 'kappa_k')
+    alpha_0, beta_0, m_0, C_0, v_0 = prior_std
+    alpha_0 = _chk(alpha_0, (K,), dt, 'alpha_0'); beta_0 = _chk(beta_0, (K,), dt, 'beta_0')
+    m_0 = _chk(m_0, (K, D), dt, 'm_0'); C_0 = _chk(C_0, (K, D, D), dt, 'C_0'); v_0 = _chk(v_0, (K,), dt, 'v_0')
+    e = lambda *s: torch.empty(*s, dtype=dt, device=dev)
+    out = (e(K), e(K), e(K, D), e(K, D, D), e(K), e(K, D), e(K, D, D), e(K))
+    lib = _lib.load()
+    nbytes = int(lib.vmp_mixture_fit_workspace_bytes(K, D))
+    work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+    _lib.call('vmp_mixture_fit', dt, N, K, D, int(is_smm), int(n_sweeps), ptr(x), ptr(alpha_0), ptr(beta_0), ptr(m_0),
+              ptr(C_0), ptr(v_0), ptr(kappa_k), ptr(r), ptr(u) if is_smm else None, *[ptr(o) for o in out], ptr(work), nbytes,
+              stream_ptr(dev), device=dev)
+    return out
+
+
+def mixture_record_len(D):
+    return int(_lib.load().vmp_mixture_record_len(int(D)))
+
+
+def mixture_prepare(stats, prior_std, is_smm, kappa_k=None, stats_next=None, out=None, want_general=False, rec=None):
+    """K-sized phase of a sweep (vmp_mixture_prepare): M-step in standard parameters from `stats` + P_k = C_k^-1 + e-step
+    constants.  Returns dict(alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi[, P_k, cst][, rec])."""
+    alpha_0, beta_0, m_0, C_0, v_0 = prior_std
+    K, D = m_0.shape
+    dt, dev = m_0.dtype, m_0.device
+    e = lambda *s: torch.empty(*s, dtype=dt, device=dev)
+    o = out if out is not None else dict(alpha_k=e(K), beta_k=e(K), m_k=e(K, D), C_k=e(K, D, D), v_k=e(K), x_k=e(K, D),
+                                         S_k=e(K, D, D), pi=e(K))
+    if want_general and 'P_k' not in o:
+        o['P_k'], o['cst'] = e(K, D, D), e(K)
+    if rec is None and not want_general:
+        rec = torch.empty(K, mixture_record_len(D), dtype=torch.float32, device=dev)
+    if rec is not None:
+        o['rec'] = rec
+    _lib.call('vmp_mixture_prepare', dt, K, D, int(bool(is_smm)), ptr(stats), ptr(stats_next), ptr(alpha_0), ptr(beta_0), ptr(m_0),
+              ptr(C_0), ptr(v_0), ptr(kappa_k), ptr(o['alpha_k']), ptr(o['beta_k']), ptr(o['m_k']), ptr(o['C_k']), ptr(o['v_k']),
+              ptr(o['x_k']), ptr(o['S_k']), ptr(o['pi']), ptr(o.get('P_k')), ptr(o.get('cst')), ptr(o.get('rec')),
+              stream_ptr(dev), device=dev)
+    return o
+
+
+def mixture_estep_fused(x, rec, is_smm, r=None, u=None, stats_next=None, write_state=True):
+    """fp32, D <= 8, K <= 32 e-step from packed records; optionally accumulates the statistics of the new state."""
+    N, D = x.shape
+    K = rec.shape[0]
+    dev = x.device
+    assert x.dtype == torch.float32 and rec.dtype == torch.float32
+    lib = _lib.load()
+    rc = lib.vmp_mixture_estep_fused_f32(N, K, D, int(bool(is_smm)), ptr(x), ptr(rec), ptr(r), ptr(u), ptr(stats_next),
+                                         int(bool(write_state)), stream_ptr(dev))
+    if rc != 0:
+        raise (ValueError if rc < 0 else _lib.VmpError)('vmp_mixture_estep_fused_f32: status %d' % rc)

@@ -168,7 +168,9 @@ template <int BS> __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
-template <int D, int BS, int WARPS, int MINB, bool TMA, int PF>
+// PADDED: the caller's dimension Dr is smaller than the engine's D (rows Dr..D-1 are an identity block); the exact-size
+// instantiation carries no run-time dimension at all.
+template <int D, int BS, int WARPS, int MINB, bool TMA, int PF, bool PADDED>
 __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const FastParams p) {
     using G = FastGeom<D, BS>;
     constexpr int ROWS = G::ROWS, GPW = 32 / BS, PPC = WARPS * GPW, LD = G::LD, REC = G::REC, TS = G::TS;
@@ -196,7 +198,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     float* ab = xb + D;                   // [D] a = L^-1 P2 d of the current pair
     float* ib = ab + D;                   // [D] 1 / L_jj of the current pair
     float* kst = ksm + (size_t)grp * p.K * 3;
-    const int K = p.K, S = p.S, Dr = p.Dr;
+    const int K = p.K, S = p.S;
+    const int Dr = PADDED ? p.Dr : D;
 
     if (tid == 0) {
         cta_acc[0] = cta_acc[1] = cta_acc[2] = cta_acc[3] = 0.0;
@@ -532,7 +535,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     }
 }
 
-template <int D, int BS, bool TMA, int PF>
+template <int D, int BS, bool TMA, int PF, bool PADDED>
 static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     using G = FastGeom<D, BS>;
     constexpr int WARPS = FastLaunch<D, BS>::WARPS, MINB = FastLaunch<D, BS>::MINB;
@@ -540,7 +543,7 @@ static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
     FastParams p = p0;
     p.ntiles = (p.N + PPC - 1) / PPC;
     const size_t smem = fast_smem_bytes<D, BS>(p.K);
-    auto kern = local_step_fast_kernel<D, BS, WARPS, MINB, TMA, PF>;
+    auto kern = local_step_fast_kernel<D, BS, WARPS, MINB, TMA, PF, PADDED>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148, occ = 1;
@@ -556,7 +559,8 @@ static int launch_fast_t(const FastParams& p0, cudaStream_t st) {
 
 #define VMP_FAST_INSTANTIATE(DD, BB)                                                  \
     template <> int launch_fast<DD, BB>(const FastParams& p, cudaStream_t st) {      \
-        return launch_fast_t<DD, BB, true, 4>(p, st);                                \
+        return p.Dr == DD ? launch_fast_t<DD, BB, true, 4, false>(p, st)             \
+                          : launch_fast_t<DD, BB, true, 4, true>(p, st);             \
     }
 #endif  // VMP_FAST_IMPL
 

@@ -1,0 +1,564 @@
+// mixture_sweep.cu — whole VB-EM sweeps of the standalone mixtures (gmm.inference gmm.py:230-269, smm.inference
+// smm.py:199-245) and the driver loops around them (gmm.py:377-379, smm.py `for i in range(nb_iters): sess.run(update)`).
+//
+// One sweep is  m_step(r[,u]) -> P = inv(C) -> e_step -> (r[,u]) .  Kernels:
+//   S  sweep_stats_kernel   : statistics [sum r, sum w, sum w x, sum w x x^T] of a GIVEN state (r, u)       (first M-step)
+//   P  sweep_prepare_kernel : K CTAs, double: M-step in standard parameters (gmm.py:25-81 / smm.py:25-85), Cholesky of C_k,
+//                             P_k = C_k^-1, the per-component E-step constants (gmm.py:117-138 / smm.py:100-128) and one packed
+//                             fp32 record per component; also zeroes the statistics buffer of the NEXT sweep
+//   E  sweep_estep_kernel   : lane <-> component (K <= 32), the component's record lives in REGISTERS for the whole kernel;
+//                             a warp streams points: x row broadcast from a per-warp staging tile, 44 FMAs for the expected
+//                             Mahalanobis distance, softmax across the lanes with shuffles, r / u written as coalesced 128-byte
+//                             rows — and, fused, the statistics of the NEW (r, u) for the next sweep's M-step, so that inside
+//                             a multi-sweep run r and u never travel through HBM (only the last sweep writes them).
+// Algorithmic HBM bytes of one sweep with state in / state out: 4 (D + 4K) per point (read x, r, u; write r, u);
+// inside vmp_mixture_fit every sweep but the last reads only x.
+// fp32, D <= 8, K <= 32 run these kernels; everything else (fp64, larger D or K, missing-data masks) goes through the
+// general kernels of suffstats.cu / mixtures.cu from the same entry point.
+#include <type_traits>
+
+#include "block_linalg.cuh"
+#include "common.cuh"
+
+namespace vmp {
+
+constexpr int SW_WARPS = 8;                 // warps per CTA of the two-CTA-per-SM kernels
+constexpr int SW_WARPS_FUSED = 12;          // e-step + statistics: ~170 registers, one CTA per SM
+constexpr int SW_RUN = 256;                 // points per fp32 partial-sum run
+constexpr float SW_LOG2E = 1.4426950408889634f;
+
+__host__ __device__ constexpr int sw_np(int D) { return D * (D + 1) / 2; }
+__host__ __device__ constexpr int sw_rs(int D) { return ((sw_np(D) + D + 4 + 3) / 4) * 4; }
+__host__ __device__ constexpr int sw_na(int D) { return (D + 1) * (D + 2) / 2; }
+
+// packed FP32x2 FMA (sm_100 FFMA2): (d0, d1) += a * (b0, b1)
+__device__ __forceinline__ void sw_ffma2_bcast(float& d0, float& d1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2,%2};\n\tmov.b64 rb, {%3,%4};\n\tmov.b64 rc, {%0,%1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0,%1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a), "f"(b0), "f"(b1));
+}
+
+// ---------------------------------------------------------------------------------------------------- P: prologue
+// stats[k] = [N_k, W_k, sum w x (D), sum w x x^T (D*D)] (double).  Outputs in T; rec (fp32 packed records) optional.
+template <typename T>
+__global__ void __launch_bounds__(128)
+sweep_prepare_kernel(int K, int D, int is_smm, const double* __restrict__ stats, double* __restrict__ stats_next,
+                     const T* __restrict__ alpha_0, const T* __restrict__ beta_0, const T* __restrict__ m_0,
+                     const T* __restrict__ C_0, const T* __restrict__ v_0, const T* __restrict__ kappa_k,
+                     T* __restrict__ alpha_k, T* __restrict__ beta_k, T* __restrict__ m_k, T* __restrict__ C_k,
+                     T* __restrict__ v_k, T* __restrict__ x_k, T* __restrict__ S_k, T* __restrict__ pi,
+                     T* __restrict__ P_k, T* __restrict__ cst, float* __restrict__ rec) {
+    extern __shared__ double sm[];
+    const int ld = D + 1;
+    double* C = sm;                 // [D][ld]  C_k -> its Cholesky factor
+    double* W = C + D * ld;         // [D][ld]  Lc^-1
+    double* xk = W + D * ld;        // [D]
+    double* mk = xk + D;            // [D]
+    double* red = mk + D;           // [32]
+    const int k = blockIdx.x, SL = stats_len(D);
+    const double* st = stats + (size_t)k * SL;
+    const double Nk = st[0], Wk = st[1];
+    const double* s1 = st + 2;
+    const double* s2 = st + 2 + D;
+    // gmm.py:30-36,42-46 NaN guard (N_k == 0 -> unnormalised sums) / smm.py:35-50 eps
+    const double den = is_smm ? Wk + 1e-20 : Wk;
+    const bool raw = !is_smm && !(Wk != 0.0);
+    const double b0 = (double)beta_0[k], bk = b0 + Wk;
+    const double vk = (double)v_0[k] + Nk + (is_smm ? 0.0 : 1.0);             // gmm.py:81 (+1) vs smm.py:76
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const double xi = raw ? s1[i] : s1[i] / den;
+        xk[i] = xi;
+        mk[i] = (b0 * (double)m_0[(size_t)k * D + i] + Wk * xi) / bk;
+        x_k[(size_t)k * D + i] = (T)xi;
+        m_k[(size_t)k * D + i] = (T)mk[i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e - i * D;
+        const double Sraw = s2[e] - xk[i] * s1[j] - s1[i] * xk[j] + Wk * xk[i] * xk[j];
+        const double S = raw ? Sraw : Sraw / den;
+        S_k[(size_t)k * D * D + e] = (T)S;
+        const double qi = xk[i] - (double)m_0[(size_t)k * D + i], qj = xk[j] - (double)m_0[(size_t)k * D + j];
+        const double c = (double)C_0[(size_t)k * D * D + e] + Wk * S + b0 * Wk / bk * qi * qj;
+        C_k[(size_t)k * D * D + e] = (T)c;
+        C[i * ld + j] = c;
+    }
+    // sum_j alpha_j of the UPDATED Dirichlet (gmm.py:134-138)
+    double sa = 0.0;
+    for (int j = threadIdx.x; j < K; j += blockDim.x) sa += (double)alpha_0[j] + stats[(size_t)j * SL];
+    sa = block_sum(sa, red);
+    __shared__ double sa_s;
+    if (threadIdx.x == 0) sa_s = sa;
+    __syncthreads();
+    sa = sa_s;
+    chol_lower_block(C, D, ld);
+    tri_inverse_block(C, W, D, ld);
+    const double ak = (double)alpha_0[k] + Nk;
+    double logdetC = 0.0;
+    for (int i = 0; i < D; ++i) logdetC += 2.0 * log(C[i * ld + i]);
+    const double logdetP = -logdetC;
+    const double elogpi = digamma_pos(ak) - digamma_pos(sa);
+    double sd = 0.0, c, hk, ek = 0.0, Dk = 0.0;
+    const double dbeta = (double)D / bk;
+    if (!is_smm) {
+        for (int i = 0; i < D; ++i) sd += digamma_pos(0.5 * (vk + 1.0 + i));                  // gmm.py:128-129
+        const double ld_guard = (logdetP > -46.051701859880914) ? logdetP : 0.0;              // det > 1e-20 (gmm.py:120-121)
+        c = elogpi + 0.5 * (sd + D * VMP_LOG_2 + ld_guard);
+        hk = 0.5;
+    } else {
+        for (int i = 0; i < D; ++i) sd += digamma_pos(0.5 * (vk + i));                        // smm.py:108
+        const double kap = (double)kappa_k[k];
+        c = lgamma(0.5 * (D + kap)) - lgamma(0.5 * kap) - 0.5 * D * log(kap * 3.14159265358979323846) + elogpi +
+            0.5 * (sd + D * VMP_LOG_2 + logdetP) + log(kap);                                  // smm.py:119-124
+        hk = 0.5 * (D + kap);
+        ek = dbeta + kap;
+        Dk = D + kap;
+    }
+    if (threadIdx.x == 0) {
+        alpha_k[k] = (T)ak;
+        beta_k[k] = (T)bk;
+        v_k[k] = (T)vk;
+        pi[k] = (T)exp(elogpi);
+        if (cst) cst[k] = (T)c;
+    }
+    // P = W^T W ; record: tri (v P, strictly-lower entries doubled) | m | c - hk D/beta | hk | D/beta + kappa | D + kappa
+    const int NP = sw_np(D), RS = sw_rs(D);
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
+        const int i = e / D, j = e - i * D;
+        const int m = i > j ? i : j;
+        double s = 0.0;
+        for (int q = m; q < D; ++q) s += W[q * ld + i] * W[q * ld + j];
+        if (P_k) P_k[(size_t)k * D * D + e] = (T)s;
+        if (rec && j <= i) rec[(size_t)k * RS + i * (i + 1) / 2 + j] = (float)(vk * (i == j ? s : 2.0 * s));
+    }
+    if (rec) {
+        for (int i = threadIdx.x; i < D; i += blockDim.x) rec[(size_t)k * RS + NP + i] = (float)mk[i];
+        if (threadIdx.x == 0) {
+            float* o = rec + (size_t)k * RS + NP + D;
+            o[0] = (float)(c - hk * dbeta);
+            o[1] = (float)hk;
+            o[2] = (float)ek;
+            o[3] = (float)Dk;
+            for (int e = NP + D + 4; e < RS; ++e) rec[(size_t)k * RS + e] = 0.f;
+        }
+    }
+    if (stats_next) for (int e = threadIdx.x; e < SL; e += blockDim.x) stats_next[(size_t)k * SL + e] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------- shared device code
+// accumulate w * xt xt^T (lower triangle of the augmented xt = [x, 1]) into acc, packed pairs
+template <int D>
+__device__ __forceinline__ void sw_accumulate(float (&acc)[sw_na(D)], const float (&xt)[D + 1], float w) {
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+        const float wx = w * xt[i];
+#pragma unroll
+        for (int j = 0; j + 1 <= i; j += 2)
+            sw_ffma2_bcast(acc[i * (i + 1) / 2 + j], acc[i * (i + 1) / 2 + j + 1], wx, xt[j], xt[j + 1]);
+        if ((i & 1) == 0) acc[i * (i + 1) / 2 + i] = fmaf(wx, xt[i], acc[i * (i + 1) / 2 + i]);
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void sw_flush(float (&acc)[sw_na(D)], float& racc, double (*red)[32], int lane) {
+    constexpr int NA = sw_na(D);
+#pragma unroll
+    for (int e = 0; e < NA; ++e) {
+        atomicAdd(&red[e][lane], (double)acc[e]);
+        acc[e] = 0.f;
+    }
+    atomicAdd(&red[NA][lane], (double)racc);
+    racc = 0.f;
+}
+
+template <int D>
+__device__ __forceinline__ void sw_store_stats(double (*red)[32], int K, bool weighted, double* __restrict__ stats) {
+    constexpr int NA = sw_na(D);
+    const int SL = stats_len(D);
+    for (int t = threadIdx.x; t < (NA + 1) * 32; t += blockDim.x) {
+        const int e = t >> 5, l = t & 31;
+        if (l >= K) continue;
+        double* out = stats + (size_t)l * SL;
+        const double v = red[e][l];
+        if (v == 0.0) continue;
+        if (e == NA) { atomicAdd(out + 0, v); continue; }          // sum r
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        const int j = e - i * (i + 1) / 2;
+        if (i < D) {
+            atomicAdd(out + 2 + D + i * D + j, v);
+            if (i != j) atomicAdd(out + 2 + D + j * D + i, v);
+        } else if (j < D) {
+            atomicAdd(out + 2 + j, v);
+        } else {
+            atomicAdd(out + 1, v);                                   // sum w
+        }
+    }
+    (void)weighted;
+}
+
+// stage the x rows of up to 32 consecutive points (contiguous 32*D floats) into the warp's tile
+template <int D>
+__device__ __forceinline__ void sw_load_x(const float* __restrict__ x, int64_t n0, int cnt, float (&pre)[D], int lane) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const int e = lane + 32 * j;
+        pre[j] = e < cnt * D ? x[n0 * D + e] : 0.f;
+    }
+}
+template <int D>
+__device__ __forceinline__ void sw_put_x(float* xs, const float (&pre)[D], int lane) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) xs[lane + 32 * j] = pre[j];
+}
+template <int D>
+__device__ __forceinline__ void sw_get_row(const float* xs, int p, float (&xt)[D + 1]) {
+    if constexpr (D % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < D / 4; ++q) {
+            const float4 v = reinterpret_cast<const float4*>(xs + p * D)[q];
+            xt[4 * q] = v.x; xt[4 * q + 1] = v.y; xt[4 * q + 2] = v.z; xt[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < D; ++i) xt[i] = xs[p * D + i];
+    }
+    xt[D] = 1.f;
+}
+
+// ---------------------------------------------------------------------------------------------------- S: statistics of a given state
+template <int D>
+__global__ void __launch_bounds__(SW_WARPS * 32, 2)
+sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ u,
+                   double* __restrict__ stats) {
+    constexpr int NA = sw_na(D);
+    __shared__ double red[NA + 1][32];
+    __shared__ __align__(16) float xsm[SW_WARPS][32 * D];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < (NA + 1) * 32; t += blockDim.x) (&red[0][0])[t] = 0.0;
+    __syncthreads();
+    const int64_t nwarps = (int64_t)gridDim.x * SW_WARPS, gw = (int64_t)blockIdx.x * SW_WARPS + wib;
+    const bool kin = lane < K;
+    const int kl = kin ? lane : 0;
+    float* xs = xsm[wib];
+    float acc[NA];
+#pragma unroll
+    for (int e = 0; e < NA; ++e) acc[e] = 0.f;
+    float racc = 0.f;
+    for (int64_t run = gw; run * SW_RUN < N; run += nwarps) {
+        const int64_t r0 = run * SW_RUN, r1 = min(N, r0 + SW_RUN);
+        for (int64_t b0 = r0; b0 < r1; b0 += 32) {
+            const int cnt = (int)min((int64_t)32, r1 - b0);
+            float pre[D];
+            sw_load_x<D>(x, b0, cnt, pre, lane);
+            __syncwarp();
+            sw_put_x<D>(xs, pre, lane);
+            __syncwarp();
+            for (int p0 = 0; p0 < cnt; p0 += 8) {
+                float rv[8], uv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const bool in = p0 + q < cnt;
+                    rv[q] = in ? r[(b0 + p0 + q) * K + kl] : 0.f;
+                    uv[q] = (in && u != nullptr) ? u[(b0 + p0 + q) * K + kl] : 1.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (p0 + q < cnt) {
+                        float xt[D + 1];
+                        sw_get_row<D>(xs, p0 + q, xt);
+                        const float rr = kin ? rv[q] : 0.f;
+                        racc += rr;
+                        sw_accumulate<D>(acc, xt, rr * uv[q]);
+                    }
+                }
+            }
+        }
+        sw_flush<D>(acc, racc, red, lane);
+    }
+    __syncthreads();
+    sw_store_stats<D>(red, K, u != nullptr, stats);
+}
+
+// ---------------------------------------------------------------------------------------------------- E: e-step (+ next statistics)
+template <int D, bool SMM, bool WRITE, bool STATS>
+__global__ void __launch_bounds__((STATS ? SW_WARPS_FUSED : SW_WARPS) * 32, STATS ? 1 : 2)
+sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* __restrict__ rec, float* __restrict__ r,
+                   float* __restrict__ u, double* __restrict__ stats) {
+    constexpr int NP = sw_np(D), RS = sw_rs(D), NA = sw_na(D), WARPS = STATS ? SW_WARPS_FUSED : SW_WARPS;
+    __shared__ double red[STATS ? NA + 1 : 1][32];
+    __shared__ __align__(16) float xsm[WARPS][32 * D];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if constexpr (STATS) {
+        for (int t = threadIdx.x; t < (NA + 1) * 32; t += blockDim.x) (&red[0][0])[t] = 0.0;
+        __syncthreads();
+    }
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS, gw = (int64_t)blockIdx.x * WARPS + wib;
+    const bool kin = lane < K;
+    float rc[RS];
+    {
+        const float4* rp = reinterpret_cast<const float4*>(rec + (size_t)(kin ? lane : 0) * RS);
+#pragma unroll
+        for (int q = 0; q < RS / 4; ++q) {
+            const float4 v = rp[q];
+            rc[4 * q] = v.x; rc[4 * q + 1] = v.y; rc[4 * q + 2] = v.z; rc[4 * q + 3] = v.w;
+        }
+    }
+    const float cp = rc[NP + D], hk = rc[NP + D + 1], ek = rc[NP + D + 2], Dk = rc[NP + D + 3];
+    float* xs = xsm[wib];
+    float acc[STATS ? NA : 1];
+#pragma unroll
+    for (int e = 0; e < (STATS ? NA : 1); ++e) acc[e] = 0.f;
+    float racc = 0.f;
+    for (int64_t run = gw; run * SW_RUN < N; run += nwarps) {
+        const int64_t r0 = run * SW_RUN, r1 = min(N, r0 + SW_RUN);
+        float pre[D];
+        sw_load_x<D>(x, r0, (int)min((int64_t)32, r1 - r0), pre, lane);
+        for (int64_t b0 = r0; b0 < r1; b0 += 32) {
+            const int cnt = (int)min((int64_t)32, r1 - b0);
+            __syncwarp();
+            sw_put_x<D>(xs, pre, lane);
+            __syncwarp();
+            if (b0 + 32 < r1) sw_load_x<D>(x, b0 + 32, (int)min((int64_t)32, r1 - b0 - 32), pre, lane);   // prefetch
+#pragma unroll 2
+            for (int p = 0; p < cnt; ++p) {
+                float xt[D + 1], d[D];
+                sw_get_row<D>(xs, p, xt);
+#pragma unroll
+                for (int i = 0; i < D; ++i) d[i] = xt[i] - rc[NP + i];
+                // q = v (x - m)^T P (x - m) in triangular form (the record's strictly-lower entries hold v (P_ic + P_ci))
+                float q = 0.f;
+#pragma unroll
+                for (int i = 0; i < D; ++i) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int c = 0; c < i; ++c) s = fmaf(rc[i * (i + 1) / 2 + c], d[c], s);
+                    q = fmaf(d[i], fmaf(rc[i * (i + 1) / 2 + i], d[i], s), q);
+                }
+                // log rho = c - hk (q + D/beta): hk = 1/2 (gmm.py:141-151) or 1/2 (D + kappa) (smm.py:122-124, linear in the distance)
+                const float lr = kin ? fmaf(-hk, q, cp) : -CUDART_INF_F;
+                const float mx = warp_max(lr);
+                const float e = exp2f((lr - mx) * SW_LOG2E);
+                const float ssum = warp_sum(e);
+                const float rr = __fdividef(e, ssum);
+                const float uu = SMM ? __fdividef(Dk, q + ek) : 1.f;                 // smm.py:131-137
+                if (WRITE && kin) {
+                    r[(b0 + p) * K + lane] = rr;
+                    if (SMM) u[(b0 + p) * K + lane] = uu;
+                }
+                if constexpr (STATS) {
+                    racc += rr;
+                    sw_accumulate<D>(acc, xt, rr * uu);
+                }
+            }
+        }
+        if constexpr (STATS) sw_flush<D>(acc, racc, red, lane);
+    }
+    if constexpr (STATS) {
+        __syncthreads();
+        sw_store_stats<D>(red, K, SMM, stats);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- host side
+static int sw_grid(const void* kern, int64_t N, int warps) {
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, 0);
+    if (occ < 1) occ = 1;
+    int64_t grid = (int64_t)sms * occ;
+    const int64_t runs = (N + SW_RUN - 1) / SW_RUN, need = (runs + warps - 1) / warps;
+    if (grid > need) grid = need;
+    return (int)(grid < 1 ? 1 : grid);
+}
+
+template <int D>
+static int sw_launch_stats(int64_t N, int K, const float* x, const float* r, const float* u, double* stats, cudaStream_t st) {
+    auto kern = sweep_stats_kernel<D>;
+    kern<<<sw_grid((const void*)kern, N, SW_WARPS), SW_WARPS * 32, 0, st>>>(N, K, x, r, u, stats);
+    return launch_status();
+}
+template <int D, bool SMM>
+static int sw_launch_estep(int64_t N, int K, const float* x, const float* rec, float* r, float* u, double* stats, bool write,
+                           cudaStream_t st) {
+#define VMP_SW_GO(W, S)                                                                                      \
+    {                                                                                                        \
+        auto kern = sweep_estep_kernel<D, SMM, W, S>;                                                        \
+        constexpr int WP = S ? SW_WARPS_FUSED : SW_WARPS;                                                    \
+        kern<<<sw_grid((const void*)kern, N, WP), WP * 32, 0, st>>>(N, K, x, rec, r, u, stats);              \
+        return launch_status();                                                                              \
+    }
+    if (write && stats) VMP_SW_GO(true, true)
+    if (write) VMP_SW_GO(true, false)
+    VMP_SW_GO(false, true)
+#undef VMP_SW_GO
+}
+
+// workspace: stats[2][K * stats_len] double | rec[K][RS] float | P_k[K,D,D] T | cst[K] T   (T counted as 8 bytes)
+size_t mixture_fit_workspace_bytes(int K, int D) {
+    return sizeof(double) * 2 * (size_t)K * stats_len(D) + sizeof(float) * (size_t)K * sw_rs(D <= 8 ? D : 8) +
+           sizeof(double) * ((size_t)K * D * D + K + 2) + 64;
+}
+
+// general kernels of suffstats.cu / mixtures.cu (fp64, D > 8, K > 32) through their C entry points
+static int gen_suffstats(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, void* st) {
+    return vmp_suffstats_f32(N, K, D, x, r, 0, u, stats, st);
+}
+static int gen_suffstats(int64_t N, int K, int D, const double* x, const double* r, const double* u, double* stats, void* st) {
+    return vmp_suffstats_f64(N, K, D, x, r, 0, u, stats, st);
+}
+static int gen_estep(int64_t N, int K, int D, const float* x, const float* a, const float* b, const float* m, const float* P,
+                     const float* v, const float* kap, float* r, float* u, float* pi, float* work, void* st) {
+    return vmp_mixture_estep_f32(N, K, D, x, a, b, m, P, v, kap, nullptr, r, u, pi, work, st);
+}
+static int gen_estep(int64_t N, int K, int D, const double* x, const double* a, const double* b, const double* m, const double* P,
+                     const double* v, const double* kap, double* r, double* u, double* pi, double* work, void* st) {
+    return vmp_mixture_estep_f64(N, K, D, x, a, b, m, P, v, kap, nullptr, r, u, pi, work, st);
+}
+
+template <typename T> struct SweepFast {
+    static int run(int64_t, int, int, int, const T*, const T*, T*, T*, double*, double*, int, bool, cudaStream_t) { return -100; }
+};
+
+template <typename T>
+int mixture_fit(int64_t N, int K, int D, int is_smm, int n_sweeps, const T* x, const T* alpha_0, const T* beta_0, const T* m_0,
+                const T* C_0, const T* v_0, const T* kappa_k, T* r, T* u, T* alpha_k, T* beta_k, T* m_k, T* C_k, T* v_k, T* x_k,
+                T* S_k, T* pi, void* work, size_t work_bytes, void* stream) {
+    if (N <= 0 || K <= 0 || n_sweeps < 1) return VMP_E_BADARG;
+    if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
+    if (!x || !alpha_0 || !beta_0 || !m_0 || !C_0 || !v_0 || !r || !alpha_k || !beta_k || !m_k || !C_k || !v_k || !x_k || !S_k ||
+        !pi || !work)
+        return VMP_E_BADARG;
+    if (is_smm && (!kappa_k || !u)) return VMP_E_BADARG;
+    if (work_bytes < mixture_fit_workspace_bytes(K, D)) return VMP_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t SLK = (size_t)K * stats_len(D);
+    double* stats[2] = {static_cast<double*>(work), static_cast<double*>(work) + SLK};
+    float* rec = reinterpret_cast<float*>(stats[1] + SLK);             // [K][RS]   (16-byte aligned: 2 K SL doubles precede it)
+    T* Pk = reinterpret_cast<T*>(reinterpret_cast<double*>(rec + (size_t)K * sw_rs(D <= 8 ? D : 8)));   // [K,D,D]
+    T* cst = Pk + (size_t)K * D * D;                                    // [K]
+    const bool fast = std::is_same<T, float>::value && D <= 8 && K <= 32;
+    cudaError_t me = cudaMemsetAsync(stats[0], 0, SLK * sizeof(double), st);
+    if (me != cudaSuccess) return (int)me;
+    const size_t psm = sizeof(double) * (2 * (size_t)D * (D + 1) + 2 * D + 40);
+    if (psm > 48 * 1024) {
+        me = cudaFuncSetAttribute(sweep_prepare_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+        if (me != cudaSuccess) return (int)me;
+    }
+    // first M-step: statistics of the caller's state
+    int rc = fast ? SweepFast<T>::run(N, K, D, 0, x, nullptr, r, is_smm ? u : nullptr, stats[0], nullptr, 0, false, st)
+                  : gen_suffstats(N, K, D, x, r, is_smm ? u : nullptr, stats[0], stream);
+    if (rc) return rc;
+    for (int s = 0; s < n_sweeps; ++s) {
+        const bool last = s + 1 == n_sweeps;
+        double* cur = stats[s & 1];
+        double* nxt = last ? nullptr : stats[(s + 1) & 1];
+        sweep_prepare_kernel<T><<<K, 128, psm, st>>>(K, D, is_smm, cur, nxt, alpha_0, beta_0, m_0, C_0, v_0,
+                                                     is_smm ? kappa_k : nullptr, alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi,
+                                                     fast ? nullptr : Pk, fast ? nullptr : cst, fast ? rec : nullptr);
+        if (int e = launch_status()) return e;
+        if (fast) {
+            rc = SweepFast<T>::run(N, K, D, 1 + (is_smm ? 1 : 0), x, reinterpret_cast<const T*>(rec), r, u, nullptr, nxt, 0, last, st);
+            if (rc) return rc;
+        } else {
+            rc = gen_estep(N, K, D, x, alpha_k, beta_k, m_k, Pk, v_k, is_smm ? kappa_k : nullptr, r, u, pi, cst, stream);
+            if (rc) return rc;
+            if (!last) {
+                rc = gen_suffstats(N, K, D, x, r, is_smm ? u : nullptr, nxt, stream);
+                if (rc) return rc;
+            }
+        }
+    }
+    return VMP_OK;
+}
+
+// mode 0: statistics of (r, u) -> stats_out; mode 1: GMM e-step; mode 2: SMM e-step (rec = packed records; stats_out = next
+// sweep's statistics or nullptr; write = store r / u)
+template <> struct SweepFast<float> {
+    static int run(int64_t N, int K, int D, int mode, const float* x, const float* rec, float* r, float* u, double* stats_in,
+                   double* stats_out, int, bool write, cudaStream_t st) {
+#define VMP_SW_CASE(DD)                                                                              \
+    case DD:                                                                                         \
+        if (mode == 0) return sw_launch_stats<DD>(N, K, x, r, u, stats_in, st);                      \
+        if (mode == 1) return sw_launch_estep<DD, false>(N, K, x, rec, r, u, stats_out, write, st);  \
+        return sw_launch_estep<DD, true>(N, K, x, rec, r, u, stats_out, write, st);
+        switch (D) {
+            VMP_SW_CASE(1) VMP_SW_CASE(2) VMP_SW_CASE(3) VMP_SW_CASE(4) VMP_SW_CASE(5) VMP_SW_CASE(6) VMP_SW_CASE(7) VMP_SW_CASE(8)
+            default: return VMP_E_BADDIM;
+        }
+#undef VMP_SW_CASE
+    }
+};
+
+// the phases of one sweep as separate calls (multi-rank sweeps all-reduce the statistics between them)
+template <typename T>
+int mixture_prepare(int K, int D, int is_smm, const double* stats, double* stats_next, const T* alpha_0, const T* beta_0,
+                    const T* m_0, const T* C_0, const T* v_0, const T* kappa_k, T* alpha_k, T* beta_k, T* m_k, T* C_k, T* v_k,
+                    T* x_k, T* S_k, T* pi, T* P_k, T* cst, float* rec, void* stream) {
+    if (K <= 0 || !stats || !alpha_0 || !beta_0 || !m_0 || !C_0 || !v_0 || !alpha_k || !beta_k || !m_k || !C_k || !v_k || !x_k ||
+        !S_k || !pi)
+        return VMP_E_BADARG;
+    if (is_smm && !kappa_k) return VMP_E_BADARG;
+    if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
+    const size_t psm = sizeof(double) * (2 * (size_t)D * (D + 1) + 2 * D + 40);
+    if (psm > 48 * 1024) {
+        cudaError_t me = cudaFuncSetAttribute(sweep_prepare_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+        if (me != cudaSuccess) return (int)me;
+    }
+    sweep_prepare_kernel<T><<<K, 128, psm, (cudaStream_t)stream>>>(K, D, is_smm, stats, stats_next, alpha_0, beta_0, m_0, C_0, v_0,
+                                                                   is_smm ? kappa_k : nullptr, alpha_k, beta_k, m_k, C_k, v_k, x_k,
+                                                                   S_k, pi, P_k, cst, rec);
+    return launch_status();
+}
+
+// fp32 D <= 8 K <= 32 statistics of a given state (called from vmp_suffstats_f32 for these shapes)
+int sweep_stats_f32(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, cudaStream_t st) {
+    if (D > 8 || K > 32) return -100;
+    return SweepFast<float>::run(N, K, D, 0, x, nullptr, const_cast<float*>(r), const_cast<float*>(u), stats, nullptr, 0, false, st);
+}
+
+}  // namespace vmp
+
+extern "C" {
+int vmp_mixture_prepare_f32(int K, int D, int is_smm, const double* stats, double* stats_next, const float* alpha_0,
+                            const float* beta_0, const float* m_0, const float* C_0, const float* v_0, const float* kappa_k,
+                            float* alpha_k, float* beta_k, float* m_k, float* C_k, float* v_k, float* x_k, float* S_k, float* pi,
+                            float* P_k, float* cst, float* rec, void* stream) {
+    return vmp::mixture_prepare<float>(K, D, is_smm, stats, stats_next, alpha_0, beta_0, m_0, C_0, v_0, kappa_k, alpha_k, beta_k, m_k,
+                                       C_k, v_k, x_k, S_k, pi, P_k, cst, rec, stream);
+}
+int vmp_mixture_prepare_f64(int K, int D, int is_smm, const double* stats, double* stats_next, const double* alpha_0,
+                            const double* beta_0, const double* m_0, const double* C_0, const double* v_0, const double* kappa_k,
+                            double* alpha_k, double* beta_k, double* m_k, double* C_k, double* v_k, double* x_k, double* S_k,
+                            double* pi, double* P_k, double* cst, float* rec, void* stream) {
+    return vmp::mixture_prepare<double>(K, D, is_smm, stats, stats_next, alpha_0, beta_0, m_0, C_0, v_0, kappa_k, alpha_k, beta_k,
+                                        m_k, C_k, v_k, x_k, S_k, pi, P_k, cst, rec, stream);
+}
+int vmp_mixture_record_len(int D) { return D <= 8 ? vmp::sw_rs(D) : 0; }
+int vmp_mixture_estep_fused_f32(int64_t N, int K, int D, int is_smm, const float* x, const float* rec, float* r, float* u,
+                                double* stats_next, int write_state, void* stream) {
+    if (N < 0 || K <= 0 || K > 32) return VMP_E_BADARG;
+    if (D < 1 || D > 8) return VMP_E_BADDIM;
+    if (N == 0) return VMP_OK;
+    if (!x || !rec || (!write_state && !stats_next) || (write_state && (!r || (is_smm && !u)))) return VMP_E_BADARG;
+    return vmp::SweepFast<float>::run(N, K, D, is_smm ? 2 : 1, x, rec, r, u, nullptr, stats_next, 0, write_state != 0,
+                                      (cudaStream_t)stream);
+}
+size_t vmp_mixture_fit_workspace_bytes(int K, int D) { return vmp::mixture_fit_workspace_bytes(K, D); }
+int vmp_mixture_fit_f32(int64_t N, int K, int D, int is_smm, int n_sweeps, const float* x, const float* alpha_0,
+                        const float* beta_0, const float* m_0, const float* C_0, const float* v_0, const float* kappa_k, float* r,
+                        float* u, float* alpha_k, float* beta_k, float* m_k, float* C_k, float* v_k, float* x_k, float* S_k,
+                        float* pi, void* workspace, size_t workspace_bytes, void* stream) {
+    return vmp::mixture_fit<float>(N, K, D, is_smm, n_sweeps, x, alpha_0, beta_0, m_0, C_0, v_0, kappa_k, r, u, alpha_k, beta_k, m_k,
+                                   C_k, v_k, x_k, S_k, pi, workspace, workspace_bytes, stream);
+}
+int vmp_mixture_fit_f64(int64_t N, int K, int D, int is_smm, int n_sweeps, const double* x, const double* alpha_0,
+                        const double* beta_0, const double* m_0, const double* C_0, const double* v_0, const double* kappa_k,
+                        double* r, double* u, double* alpha_k, double* beta_k, double* m_k, double* C_k, double* v_k, double* x_k,
+                        double* S_k, double* pi, void* workspace, size_t workspace_bytes, void* stream) {
+    return vmp::mixture_fit<double>(N, K, D, is_smm, n_sweeps, x, alpha_0, beta_0, m_0, C_0, v_0, kappa_k, r, u, alpha_k, beta_k,
+                                    m_k, C_k, v_k, x_k, S_k, pi, workspace, workspace_bytes, stream);
+}
+}

@@ -304,6 +304,17 @@ int suffstats_tc_dispatch<float>(int64_t N, int K, int D, const float* x, const 
     return suffstats_tc(N, K, D, x, r, r_is_log, stats, st);
 }
 
+// fp32, D <= 8, K <= 32, plain responsibilities: the lane <-> component kernel of mixture_sweep.cu
+int sweep_stats_f32(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, cudaStream_t st);
+template <typename T>
+static int sweep_stats_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, cudaStream_t) { return -100; }
+template <>
+int sweep_stats_dispatch<float>(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
+                                double* stats, cudaStream_t st) {
+    if (r_is_log || D > 8 || K > 32) return -100;
+    return sweep_stats_f32(N, K, D, x, r, u_nk, stats, st);
+}
+
 template <typename T>
 int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
               void* stream) {
@@ -311,6 +322,7 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     if (N == 0) return VMP_OK;
     if (!x || !r || !stats) return VMP_E_BADARG;
+    if (int rc = sweep_stats_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream); rc != -100) return rc;
     if (int rc = suffstats_tc_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream); rc != -100) return rc;
 #define VMP_SSM(DD) \
     case DD: return launch_suffstats_small<T, DD>(N, K, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream)

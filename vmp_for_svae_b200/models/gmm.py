@@ -8,6 +8,7 @@ tensor expressions.
 import torch
 
 from .. import core
+from ..lazy import lazy_log
 from ..distributions import dirichlet, niw
 from . import svae
 
@@ -116,15 +117,25 @@ def _prior_standard(K, D, seed, dtype, device):
 def inference(x, K, seed, name='inference', *, r_nk=None, dtype=None):
     """gmm.py:230-269 : one VB-EM sweep.  The reference keeps r_nk in a tf.Variable initialised from Dirichlet(1);
     here the state tensor is passed in (`r_nk=`, updated IN PLACE) or created on first use.
-    Returns (r_nk (state, updated), log_r_nk, theta, (x_k, S_k, pi))."""
+    Returns (r_nk (state, updated), log_r_nk (deferred: a graph node in the reference), theta, (x_k, S_k, pi))."""
     N, D = x.shape
     if r_nk is None:
         g = torch.Generator(device='cpu').manual_seed(int(seed))
         e = -torch.log(torch.rand(N, K, generator=g, dtype=torch.float64))
         r_nk = (e / e.sum(1, keepdim=True)).to(device=x.device, dtype=x.dtype).contiguous()
-    alpha_0, beta_0, m_0, C_0, v_0 = _prior_standard(K, D, seed, x.dtype, x.device)
-    alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k = m_step(x, r_nk, alpha_0, beta_0.contiguous(), m_0.contiguous(),
-                                                      C_0.contiguous(), v_0.contiguous())
-    P_k, _ = core.spd_inverse(C_k, want_logdet=False)
-    _, _, pi = core.mixture_estep(x, alpha_k, beta_k, m_k, P_k, v_k, r=r_nk)
-    return r_nk, torch.log(r_nk), (alpha_k, beta_k, m_k, C_k, v_k), (x_k, S_k, pi)
+    alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi = core.mixture_fit(x, r_nk, None, _prior_standard(K, D, seed, x.dtype, x.device))
+    return r_nk, lazy_log(r_nk), (alpha_k, beta_k, m_k, C_k, v_k), (x_k, S_k, pi)
+
+
+def fit(x, K, seed, nb_iters, *, r_nk=None):
+    """The reference's driver loop (gmm.py:377-379: `for i in range(nb_iters): sess.run(update)`) as ONE call: nb_iters sweeps
+    of `inference` on the state r_nk.  In fp32 with D <= 8, K <= 32 the responsibilities stay on chip between sweeps (the
+    e-step kernel accumulates the next M-step's statistics); only the final state is written.  Same return as inference."""
+    N, D = x.shape
+    if r_nk is None:
+        g = torch.Generator(device='cpu').manual_seed(int(seed))
+        e = -torch.log(torch.rand(N, K, generator=g, dtype=torch.float64))
+        r_nk = (e / e.sum(1, keepdim=True)).to(device=x.device, dtype=x.dtype).contiguous()
+    alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi = core.mixture_fit(x, r_nk, None, _prior_standard(K, D, seed, x.dtype, x.device),
+                                                                    n_sweeps=int(nb_iters))
+    return r_nk, lazy_log(r_nk), (alpha_k, beta_k, m_k, C_k, v_k), (x_k, S_k, pi)

@@ -6,6 +6,7 @@ Same kernels as models.gmm with the scale variables u_nk: moments weighted by r*
 import torch
 
 from .. import core
+from ..lazy import lazy_log
 from ..distributions import dirichlet, niw
 from . import svae
 
@@ -118,10 +119,24 @@ def inference(x, K, kappa_init, seed, name='inference', *, r_nk=None, u_nk=None)
         r_nk = (e / e.sum(1, keepdim=True)).to(device=x.device, dtype=x.dtype).contiguous()
     if u_nk is None:
         u_nk = torch.ones(N, K, dtype=x.dtype, device=x.device)
-    alpha_0, beta_0, m_0, C_0, v_0 = _prior_standard(K, D, seed, x.dtype, x.device)
     kappa_k = kappa_init * torch.ones(K, dtype=x.dtype, device=x.device)
-    alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k = m_step(x, r_nk, u_nk, alpha_0, beta_0.contiguous(), m_0.contiguous(),
-                                                      C_0.contiguous(), v_0.contiguous())
-    P_k, _ = core.spd_inverse(C_k, want_logdet=False)
-    _, _, pi = core.mixture_estep(x, alpha_k, beta_k, m_k, P_k, v_k, kappa_k=kappa_k, r=r_nk, u_out=u_nk)
-    return (r_nk, u_nk), torch.log(r_nk), (alpha_k, beta_k, m_k, C_k, v_k, kappa_k), (x_k, S_k, pi)
+    alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi = core.mixture_fit(x, r_nk, u_nk, _prior_standard(K, D, seed, x.dtype, x.device),
+                                                                    kappa_k=kappa_k)
+    return (r_nk, u_nk), lazy_log(r_nk), (alpha_k, beta_k, m_k, C_k, v_k, kappa_k), (x_k, S_k, pi)
+
+
+def fit(x, K, kappa_init, seed, nb_iters, *, r_nk=None, u_nk=None):
+    """The reference's driver loop (smm.py __main__: `for i in range(nb_iters): sess.run(update)`) as ONE call: nb_iters sweeps
+    of `inference` on the state (r_nk, u_nk).  In fp32 with D <= 8, K <= 32 r and u stay on chip between sweeps (the e-step
+    kernel accumulates the next M-step's statistics); only the final state is written.  Same return as inference."""
+    N, D = x.shape
+    if r_nk is None:
+        g = torch.Generator(device='cpu').manual_seed(int(seed))
+        e = -torch.log(torch.rand(N, K, generator=g, dtype=torch.float64))
+        r_nk = (e / e.sum(1, keepdim=True)).to(device=x.device, dtype=x.dtype).contiguous()
+    if u_nk is None:
+        u_nk = torch.ones(N, K, dtype=x.dtype, device=x.device)
+    kappa_k = kappa_init * torch.ones(K, dtype=x.dtype, device=x.device)
+    alpha_k, beta_k, m_k, C_k, v_k, x_k, S_k, pi = core.mixture_fit(x, r_nk, u_nk, _prior_standard(K, D, seed, x.dtype, x.device),
+                                                                    kappa_k=kappa_k, n_sweeps=int(nb_iters))
+    return (r_nk, u_nk), lazy_log(r_nk), (alpha_k, beta_k, m_k, C_k, v_k, kappa_k), (x_k, S_k, pi)

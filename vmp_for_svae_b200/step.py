@@ -103,10 +103,11 @@ class SVAEStep(object):
 
 
 def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, staging=None, chunk=None, noise=None,
-                   u=None):
+                   u=None, copy_back=None):
     """End-to-end form of the step for HOST-resident encoder outputs (pinned CPU tensors): copies this rank's
-    eta1 / eta2_diag to the device, runs the step, and reads the step's results (ELBO terms and the updated theta's
-    alpha) back to the host.  Returns (elbo_terms ndarray[4], alpha ndarray[K]).
+    eta1 / eta2_diag to the device, runs the step, and reads the step's results back to the host: the ELBO terms and all
+    five updated global natural parameters; with copy_back=(log_r_host[N,K], x_sample_host[N,D]) (pinned) also the per-point
+    outputs.  Returns (elbo_terms ndarray[4], [alpha, A, b, beta, v_hat] as CPU tensors).
 
     chunk=None: one copy, then `stepper.step`.  chunk=C (points): the shard is processed in chunks of C points with the
     host->device copy of chunk c+1 (own stream, two staging slots) overlapping the local step + statistics of chunk c;
@@ -159,6 +160,9 @@ def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, st
             torch.distributed.all_reduce(st.red, group=st.pg)
         core.ng_update(st.stats, rho, prior, theta)
         out = dict(elbo_acc=st.elbo_acc)
+    if copy_back is not None:
+        copy_back[0].copy_(st.log_r, non_blocking=True)
+        copy_back[1].copy_(st.x_sample, non_blocking=True)
+    theta_h = [t.to('cpu') for t in theta]
     elbo = out['elbo_acc'].to('cpu', non_blocking=False)
-    alpha = theta[0].to('cpu')
-    return elbo.numpy(), alpha.numpy()
+    return elbo.numpy(), theta_h
