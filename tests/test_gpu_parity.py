@@ -483,7 +483,8 @@ def test_sharded_mixture_sweep_equals_fit(dt):
     full = core.suffstats(x, r0, u_nk=torch.ones_like(r0))
     parts = core.suffstats(x[:cut].contiguous(), r0[:cut].contiguous(), u_nk=torch.ones_like(r0[:cut])) + \
         core.suffstats(x[cut:].contiguous(), r0[cut:].contiguous(), u_nk=torch.ones_like(r0[cut:]))
-    torch.testing.assert_close(parts, full, rtol=1e-6 if dt == torch.float32 else 1e-12, atol=1e-6)
+    # fp32 partial sums cover runs of <= 256 points whose boundaries move with the shard cut: compare at the block's scale
+    assert float((parts - full).abs().max()) <= (2e-6 if dt == torch.float32 else 1e-12) * float(full.abs().max())
 
 
 @pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])

@@ -23,7 +23,7 @@
 namespace vmp {
 
 constexpr int SW_WARPS = 8;                 // warps per CTA of the two-CTA-per-SM kernels
-constexpr int SW_WARPS_FUSED = 12;          // e-step + statistics: ~170 registers, one CTA per SM
+constexpr int SW_WARPS_FUSED = 8;           // e-step + statistics: ~200 registers, one CTA per SM (8 independent chains per warp)
 constexpr int SW_RUN = 256;                 // points per fp32 partial-sum run
 constexpr float SW_LOG2E = 1.4426950408889634f;
 
@@ -38,6 +38,41 @@ __device__ __forceinline__ void sw_ffma2_bcast(float& d0, float& d1, float a, fl
         : "+f"(d0), "+f"(d1)
         : "f"(a), "f"(b0), "f"(b1));
 }
+
+// (d0, d1) += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void sw_ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%5};\n\tmov.b64 rc, {%0,%1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0,%1}, rc;\n\t}"
+        : "+f"(d0), "+f"(d1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// (d0, d1) = (a0, a1) + (b, b)
+__device__ __forceinline__ void sw_fadd2_bcast(float& d0, float& d1, float a0, float a1, float b) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2,%3};\n\tmov.b64 rb, {%4,%4};\n\t"
+        "add.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0,%1}, rc;\n\t}"
+        : "=f"(d0), "=f"(d1)
+        : "f"(a0), "f"(a1), "f"(b));
+}
+// warp-wide float max in ONE instruction: order-preserving map to int32 + REDUX.MAX.S32
+__device__ __forceinline__ float sw_warp_max(float v) {
+    int k = __float_as_int(v);
+    k = k >= 0 ? k : k ^ 0x7fffffff;
+    k = __reduce_max_sync(0xffffffffu, k);
+    k = k >= 0 ? k : k ^ 0x7fffffff;
+    return __int_as_float(k);
+}
+__device__ __forceinline__ float sw_ex2(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void sw_cp_async16(float* dst, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 16 : 0;                                   // src-size 0: zero-fill, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void sw_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void sw_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------------- P: prologue
 // stats[k] = [N_k, W_k, sum w x (D), sum w x x^T (D*D)] (double).  Outputs in T; rec (fp32 packed records) optional.
@@ -122,7 +157,8 @@ sweep_prepare_kernel(int K, int D, int is_smm, const double* __restrict__ stats,
         pi[k] = (T)exp(elogpi);
         if (cst) cst[k] = (T)c;
     }
-    // P = W^T W ; record: tri (v P, strictly-lower entries doubled) | m | c - hk D/beta | hk | D/beta + kappa | D + kappa
+    // P = W^T W ; record: tri (v P, strictly-lower entries doubled) | -m | log2(e) (c - hk D/beta) | log2(e) hk |
+    // D/beta + kappa | D + kappa     (the e-step evaluates the soft-max in base 2: one FFMA + one MUFU.EX2 per pair)
     const int NP = sw_np(D), RS = sw_rs(D);
     for (int e = threadIdx.x; e < D * D; e += blockDim.x) {
         const int i = e / D, j = e - i * D;
@@ -133,11 +169,11 @@ sweep_prepare_kernel(int K, int D, int is_smm, const double* __restrict__ stats,
         if (rec && j <= i) rec[(size_t)k * RS + i * (i + 1) / 2 + j] = (float)(vk * (i == j ? s : 2.0 * s));
     }
     if (rec) {
-        for (int i = threadIdx.x; i < D; i += blockDim.x) rec[(size_t)k * RS + NP + i] = (float)mk[i];
+        for (int i = threadIdx.x; i < D; i += blockDim.x) rec[(size_t)k * RS + NP + i] = (float)(-mk[i]);
         if (threadIdx.x == 0) {
             float* o = rec + (size_t)k * RS + NP + D;
-            o[0] = (float)(c - hk * dbeta);
-            o[1] = (float)hk;
+            o[0] = (float)(1.4426950408889634074 * (c - hk * dbeta));
+            o[1] = (float)(1.4426950408889634074 * hk);
             o[2] = (float)ek;
             o[3] = (float)Dk;
             for (int e = NP + D + 4; e < RS; ++e) rec[(size_t)k * RS + e] = 0.f;
@@ -228,43 +264,82 @@ __device__ __forceinline__ void sw_get_row(const float* xs, int p, float (&xt)[D
 }
 
 // ---------------------------------------------------------------------------------------------------- S: statistics of a given state
-template <int D>
+// ASYNC: the r / u rows of 8 points at a time are staged through a per-warp 3-deep cp.async ring (16-byte copies: needs
+// K % 4 == 0 and 16-byte aligned r / u), so ~4 KB per warp are in flight while the previous group is accumulated; the plain
+// variant loads them straight into registers.
+template <int D, bool ASYNC>
 __global__ void __launch_bounds__(SW_WARPS * 32, 2)
 sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ u,
                    double* __restrict__ stats) {
-    constexpr int NA = sw_na(D);
+    constexpr int NA = sw_na(D), GP = 8, NST = 3;
     __shared__ double red[NA + 1][32];
     __shared__ __align__(16) float xsm[SW_WARPS][32 * D];
+    extern __shared__ __align__(16) float ring_raw[];                // ASYNC: [SW_WARPS][NST][2][GP * 32]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float* ring_w = ring_raw + (size_t)wib * NST * 2 * GP * 32;
     for (int t = threadIdx.x; t < (NA + 1) * 32; t += blockDim.x) (&red[0][0])[t] = 0.0;
     __syncthreads();
     const int64_t nwarps = (int64_t)gridDim.x * SW_WARPS, gw = (int64_t)blockIdx.x * SW_WARPS + wib;
-    const bool kin = lane < K;
+    const bool kin = lane < K, has_u = u != nullptr;
     const int kl = kin ? lane : 0;
     float* xs = xsm[wib];
     float acc[NA];
 #pragma unroll
     for (int e = 0; e < NA; ++e) acc[e] = 0.f;
     float racc = 0.f;
+    constexpr int GPR = SW_RUN / GP;                                 // groups per run
+    // linear group counter c of this warp -> first point of the group (runs are strided over the warps of the grid)
+    auto group_point = [&](int64_t c) -> int64_t { return (gw + (c / GPR) * nwarps) * SW_RUN + (c % GPR) * GP; };
+    auto issue = [&](int64_t c) {
+        if constexpr (ASYNC) {
+            const int64_t n0 = group_point(c);
+            float* dst = ring_w + (c % NST) * 2 * GP * 32;
+            const int chunks = GP * K / 4;                           // 16-byte chunks of GP consecutive rows
+            for (int e = lane; e < chunks; e += 32) {
+                const bool ok = n0 + (4 * e) / K < N;
+                sw_cp_async16(dst + 4 * e, ok ? r + n0 * K + 4 * e : r, ok);
+                if (has_u) sw_cp_async16(dst + GP * 32 + 4 * e, ok ? u + n0 * K + 4 * e : u, ok);
+            }
+            sw_cp_commit();
+        }
+    };
+    if constexpr (ASYNC) { issue(0); issue(1); }
+    int64_t c = 0;
     for (int64_t run = gw; run * SW_RUN < N; run += nwarps) {
         const int64_t r0 = run * SW_RUN, r1 = min(N, r0 + SW_RUN);
-        for (int64_t b0 = r0; b0 < r1; b0 += 32) {
-            const int cnt = (int)min((int64_t)32, r1 - b0);
-            float pre[D];
-            sw_load_x<D>(x, b0, cnt, pre, lane);
-            __syncwarp();
-            sw_put_x<D>(xs, pre, lane);
-            __syncwarp();
-            for (int p0 = 0; p0 < cnt; p0 += 8) {
-                float rv[8], uv[8];
+        for (int64_t b0 = r0; b0 < r0 + SW_RUN; b0 += 32) {
+            const int cnt = (int)max((int64_t)0, min((int64_t)32, r1 - b0));
+            if (cnt > 0) {
+                float pre[D];
+                sw_load_x<D>(x, b0, cnt, pre, lane);
+                __syncwarp();
+                sw_put_x<D>(xs, pre, lane);
+                __syncwarp();
+            }
+#pragma unroll 1
+            for (int p0 = 0; p0 < 32; p0 += GP, ++c) {
+                float rv[GP], uv[GP];
+                if constexpr (ASYNC) {
+                    issue(c + 2);
+                    sw_cp_wait<2>();
+                    __syncwarp();
+                    const float* src = ring_w + (c % NST) * 2 * GP * 32;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const bool in = p0 + q < cnt;
-                    rv[q] = in ? r[(b0 + p0 + q) * K + kl] : 0.f;
-                    uv[q] = (in && u != nullptr) ? u[(b0 + p0 + q) * K + kl] : 1.f;
+                    for (int q = 0; q < GP; ++q) {
+                        rv[q] = src[q * K + kl];
+                        uv[q] = has_u ? src[GP * 32 + q * K + kl] : 1.f;
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int q = 0; q < GP; ++q) {
+                        const bool in = p0 + q < cnt;
+                        rv[q] = in ? r[(b0 + p0 + q) * K + kl] : 0.f;
+                        uv[q] = (in && has_u) ? u[(b0 + p0 + q) * K + kl] : 1.f;
+                    }
                 }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
+                for (int q = 0; q < GP; ++q) {
                     if (p0 + q < cnt) {
                         float xt[D + 1];
                         sw_get_row<D>(xs, p0 + q, xt);
@@ -277,16 +352,19 @@ sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
         }
         sw_flush<D>(acc, racc, red, lane);
     }
+    if constexpr (ASYNC) sw_cp_wait<0>();
     __syncthreads();
     sw_store_stats<D>(red, K, u != nullptr, stats);
 }
 
 // ---------------------------------------------------------------------------------------------------- E: e-step (+ next statistics)
+// Points are processed in groups of GP = 8 (four packed pairs): the eight score chains, the eight soft-max reductions and the
+// eight normalisations are independent, so the shuffle / MUFU latencies overlap instead of serialising per point.
 template <int D, bool SMM, bool WRITE, bool STATS>
 __global__ void __launch_bounds__((STATS ? SW_WARPS_FUSED : SW_WARPS) * 32, STATS ? 1 : 2)
 sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* __restrict__ rec, float* __restrict__ r,
                    float* __restrict__ u, double* __restrict__ stats) {
-    constexpr int NP = sw_np(D), RS = sw_rs(D), NA = sw_na(D), WARPS = STATS ? SW_WARPS_FUSED : SW_WARPS;
+    constexpr int NP = sw_np(D), RS = sw_rs(D), NA = sw_na(D), WARPS = STATS ? SW_WARPS_FUSED : SW_WARPS, GP = 8;
     __shared__ double red[STATS ? NA + 1 : 1][32];
     __shared__ __align__(16) float xsm[WARPS][32 * D];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -305,7 +383,7 @@ sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
             rc[4 * q] = v.x; rc[4 * q + 1] = v.y; rc[4 * q + 2] = v.z; rc[4 * q + 3] = v.w;
         }
     }
-    const float cp = rc[NP + D], hk = rc[NP + D + 1], ek = rc[NP + D + 2], Dk = rc[NP + D + 3];
+    const float cp2 = rc[NP + D], hk2 = rc[NP + D + 1], ek = rc[NP + D + 2], Dk = rc[NP + D + 3];
     float* xs = xsm[wib];
     float acc[STATS ? NA : 1];
 #pragma unroll
@@ -321,35 +399,62 @@ sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
             sw_put_x<D>(xs, pre, lane);
             __syncwarp();
             if (b0 + 32 < r1) sw_load_x<D>(x, b0 + 32, (int)min((int64_t)32, r1 - b0 - 32), pre, lane);   // prefetch
-#pragma unroll 2
-            for (int p = 0; p < cnt; ++p) {
-                float xt[D + 1], d[D];
-                sw_get_row<D>(xs, p, xt);
+#pragma unroll 1
+            for (int p0 = 0; p0 < cnt; p0 += GP) {
+                // ---- scores of GP points: q = v (x - m)^T P (x - m) in triangular form, two points per packed FFMA2
+                float qv[GP];
 #pragma unroll
-                for (int i = 0; i < D; ++i) d[i] = xt[i] - rc[NP + i];
-                // q = v (x - m)^T P (x - m) in triangular form (the record's strictly-lower entries hold v (P_ic + P_ci))
-                float q = 0.f;
+                for (int pp = 0; pp < GP / 2; ++pp) {
+                    const int pa = min(p0 + 2 * pp, cnt - 1), pb = min(p0 + 2 * pp + 1, cnt - 1);     // clamped: tail rows repeat
+                    float xa[D + 1], xb[D + 1], da[D], db[D];
+                    sw_get_row<D>(xs, pa, xa);
+                    sw_get_row<D>(xs, pb, xb);
 #pragma unroll
-                for (int i = 0; i < D; ++i) {
-                    float s = 0.f;
+                    for (int i = 0; i < D; ++i) sw_fadd2_bcast(da[i], db[i], xa[i], xb[i], rc[NP + i]);   // x - m (record holds -m)
+                    float qa = 0.f, qb = 0.f;
 #pragma unroll
-                    for (int c = 0; c < i; ++c) s = fmaf(rc[i * (i + 1) / 2 + c], d[c], s);
-                    q = fmaf(d[i], fmaf(rc[i * (i + 1) / 2 + i], d[i], s), q);
+                    for (int i = 0; i < D; ++i) {
+                        float sa = 0.f, sb = 0.f;
+#pragma unroll
+                        for (int c2 = 0; c2 < i; ++c2) sw_ffma2_bcast(sa, sb, rc[i * (i + 1) / 2 + c2], da[c2], db[c2]);
+                        sw_ffma2_bcast(sa, sb, rc[i * (i + 1) / 2 + i], da[i], db[i]);
+                        sw_ffma2(qa, qb, da[i], db[i], sa, sb);
+                    }
+                    qv[2 * pp] = qa;
+                    qv[2 * pp + 1] = qb;
                 }
-                // log rho = c - hk (q + D/beta): hk = 1/2 (gmm.py:141-151) or 1/2 (D + kappa) (smm.py:122-124, linear in the distance)
-                const float lr = kin ? fmaf(-hk, q, cp) : -CUDART_INF_F;
-                const float mx = warp_max(lr);
-                const float e = exp2f((lr - mx) * SW_LOG2E);
-                const float ssum = warp_sum(e);
-                const float rr = __fdividef(e, ssum);
-                const float uu = SMM ? __fdividef(Dk, q + ek) : 1.f;                 // smm.py:131-137
-                if (WRITE && kin) {
-                    r[(b0 + p) * K + lane] = rr;
-                    if (SMM) u[(b0 + p) * K + lane] = uu;
+                // ---- soft-max over the components (lanes), base 2: log2 rho = cp2 - hk2 q  (gmm.py:141-151, smm.py:122-128)
+                float ev[GP];
+#pragma unroll
+                for (int g = 0; g < GP; ++g) {
+                    const float l2 = kin ? fmaf(-hk2, qv[g], cp2) : -CUDART_INF_F;
+                    ev[g] = sw_ex2(l2 - sw_warp_max(l2));
                 }
-                if constexpr (STATS) {
-                    racc += rr;
-                    sw_accumulate<D>(acc, xt, rr * uu);
+                float sv[GP];
+#pragma unroll
+                for (int g = 0; g < GP; ++g) sv[g] = ev[g];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int g = 0; g < GP; ++g) sv[g] += __shfl_xor_sync(0xffffffffu, sv[g], o);
+                }
+#pragma unroll
+                for (int g = 0; g < GP; ++g) {
+                    const int p = p0 + g;
+                    const float rr = __fdividef(ev[g], sv[g]);
+                    const float uu = SMM ? __fdividef(Dk, qv[g] + ek) : 1.f;                 // smm.py:131-137
+                    const bool live = p < cnt;
+                    if (WRITE && kin && live) {
+                        r[(b0 + p) * K + lane] = rr;
+                        if (SMM) u[(b0 + p) * K + lane] = uu;
+                    }
+                    if constexpr (STATS) {
+                        float xt[D + 1];
+                        sw_get_row<D>(xs, min(p, cnt - 1), xt);
+                        const float rl = live ? rr : 0.f;
+                        racc += rl;
+                        sw_accumulate<D>(acc, xt, rl * uu);
+                    }
                 }
             }
         }
@@ -362,11 +467,11 @@ sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------------- host side
-static int sw_grid(const void* kern, int64_t N, int warps) {
+static int sw_grid(const void* kern, int64_t N, int warps, size_t dyn_smem = 0) {
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, dyn_smem);
     if (occ < 1) occ = 1;
     int64_t grid = (int64_t)sms * occ;
     const int64_t runs = (N + SW_RUN - 1) / SW_RUN, need = (runs + warps - 1) / warps;
@@ -376,8 +481,17 @@ static int sw_grid(const void* kern, int64_t N, int warps) {
 
 template <int D>
 static int sw_launch_stats(int64_t N, int K, const float* x, const float* r, const float* u, double* stats, cudaStream_t st) {
-    auto kern = sweep_stats_kernel<D>;
-    kern<<<sw_grid((const void*)kern, N, SW_WARPS), SW_WARPS * 32, 0, st>>>(N, K, x, r, u, stats);
+    const bool aligned = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(u)) % 16 == 0);
+    if (aligned) {
+        auto kern = sweep_stats_kernel<D, true>;
+        constexpr int ring_bytes = SW_WARPS * 3 * 2 * 8 * 32 * (int)sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);
+        if (e != cudaSuccess) return (int)e;
+        kern<<<sw_grid((const void*)kern, N, SW_WARPS, ring_bytes), SW_WARPS * 32, ring_bytes, st>>>(N, K, x, r, u, stats);
+    } else {
+        auto kern = sweep_stats_kernel<D, false>;
+        kern<<<sw_grid((const void*)kern, N, SW_WARPS), SW_WARPS * 32, 0, st>>>(N, K, x, r, u, stats);
+    }
     return launch_status();
 }
 template <int D, bool SMM>
