@@ -151,6 +151,21 @@ int vmp_suffstats_f32(int64_t N, int K, int D, const float* x, const float* r, i
 int vmp_suffstats_f64(int64_t N, int K, int D, const double* x, const double* r, int r_is_log,
                       const double* u_nk, double* stats, void* stream);
 
+/* Statistics + natural-gradient update in ONE launch (single-GPU path; north_star: "the NIW/Dirichlet natural-gradient
+ * step is fused into the tail of that reduction"): as vmp_suffstats_*, and the CTA that finishes last applies
+ * theta <- (1-rho) theta + rho (prior + stats terms) exactly as vmp_ng_update_* (svae.py:154-176, 376-403).
+ * counter: one device uint32, zero before the first call (the kernel resets it); stats is accumulated into as usual and
+ * holds the statistics afterwards.  With several ranks use vmp_suffstats_* + all-reduce + vmp_ng_update_*.            */
+int vmp_suffstats_update_f32(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
+                             double* stats, unsigned int* counter, double rho, const double* rho_dev, int only_alpha,
+                             const float* p_alpha, const float* p_A, const float* p_b, const float* p_beta,
+                             const float* p_vhat, float* alpha, float* A, float* b, float* beta, float* v_hat, void* stream);
+int vmp_suffstats_update_f64(int64_t N, int K, int D, const double* x, const double* r, int r_is_log, const double* u_nk,
+                             double* stats, unsigned int* counter, double rho, const double* rho_dev, int only_alpha,
+                             const double* p_alpha, const double* p_A, const double* p_b, const double* p_beta,
+                             const double* p_vhat, double* alpha, double* A, double* b, double* beta, double* v_hat,
+                             void* stream);
+
 /* ---- natural-gradient (CVI) update ------------------------------------------------------------------
  * Replaces svae.m_step (svae.py:154-176) + svae.update_gmm_params (376-403):
  * theta* = prior + [N_k, sum r x x^T, sum r x, N_k, N_k + 1]; theta <- (1-rho) theta + rho theta*, in place.

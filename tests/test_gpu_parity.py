@@ -668,6 +668,35 @@ def test_tensor_core_suffstats_equals_fp32_kernel_and_fp64(N, r_is_log):
     assert torch.equal(S, S.transpose(1, 2))            # mirrored lower triangle: exactly symmetric
 
 
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('shape', [(3000, 12, 64), (2000, 7, 64), (1500, 9, 32), (4000, 10, 6), (900, 40, 3), (50, 3, 2)],
+                         ids=lambda s: 'N%dK%dD%d' % s)
+@pytest.mark.parametrize('only_alpha', [False, True], ids=['theta', 'alpha'])
+def test_fused_statistics_update_equals_two_launches(shape, dt, only_alpha):
+    """vmp_suffstats_update (the natural-gradient step in the tail of the reduction: tensor-core, FP32, small-D and sweep
+    statistics kernels) == vmp_suffstats + vmp_ng_update, bit for bit, repeatedly (the ticket counter re-arms itself)."""
+    from vmp_for_svae_b200 import core
+    N, K, D = shape
+    rs = np.random.RandomState(N + D)
+    x = T(rs.randn(N, D), dt, DEV)
+    log_r = torch.log_softmax(T(2.0 * rs.randn(N, K), dt, DEV), dim=1).contiguous()
+    prior, theta, _, _, _, _ = _oracle_inputs(4, K, D, 1, seed=D, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    pr, th_a, th_b = dev(prior), dev(theta), dev(theta)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for it in range(3):
+        sa = core.suffstats(x, log_r, r_is_log=True)
+        core.ng_update(sa, 0.3, [pr[0]] if only_alpha else pr, [th_a[0]] if only_alpha else th_a, only_alpha=only_alpha)
+        sb = torch.zeros_like(sa)
+        core.suffstats_update(x, log_r, sb, counter, 0.3, [pr[0]] if only_alpha else pr, [th_b[0]] if only_alpha else th_b,
+                              r_is_log=True, only_alpha=only_alpha)
+        torch.cuda.synchronize()
+        assert int(counter.item()) == 0
+        torch.testing.assert_close(sb, sa, rtol=1e-12, atol=1e-9)          # atomics: summation order may differ
+        for a, b in zip(th_a, th_b):
+            torch.testing.assert_close(b, a, rtol=1e-6 if dt == torch.float32 else 1e-12, atol=1e-7)
+
+
 def test_graphed_step_matches_eager_statistics():
     """SVAEStep.make_graph: replays move theta exactly like eager steps fed the same (graph-drawn) noise cannot be
     compared draw by draw, so check the invariants: N_k sums to N, theta stays finite and moves toward the statistics,

@@ -25,6 +25,7 @@ _SIGS_T = {
                                [c_ptr, ctypes.c_size_t, c_ptr],
     'vmp_fill_noise': [c_i64, c_int, c_int, c_int, c_u64, c_i64, c_ptr, c_ptr, c_ptr],
     'vmp_suffstats': [c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr],
+    'vmp_suffstats_update': [c_i64, c_int, c_int, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_ptr, c_dbl, c_ptr, c_int] + [c_ptr] * 10 + [c_ptr],
     'vmp_ng_update': [c_int, c_int, c_ptr, c_dbl, c_ptr, c_int] + [c_ptr] * 15 + [c_ptr],
     'vmp_mixture_mstep': [c_int, c_int, c_int, c_ptr] + [c_ptr] * 12 + [c_ptr],
     'vmp_mixture_estep': [c_i64, c_int, c_int] + [c_ptr] * 12 + [c_ptr],

@@ -160,6 +160,31 @@ def suffstats(x, r, r_is_log=False, u_nk=None, stats=None):
     return stats
 
 
+def suffstats_update(x, r, stats, counter, rho, prior, theta, r_is_log=False, u_nk=None, only_alpha=False):
+    """Statistics + natural-gradient update in one launch (vmp_suffstats_update; single-GPU path): stats += [...] and the last
+    CTA applies theta <- (1-rho) theta + rho (prior + stats terms) in place.  counter: 1-element int32 CUDA tensor, zero."""
+    N, D = x.shape
+    K = r.shape[1]
+    dt, dev = x.dtype, x.device
+    x = _chk(x, (N, D), dt, 'x'); r = _chk(r, (N, K), dt, 'r_nk')
+    rho_dev = None
+    if isinstance(rho, torch.Tensor):
+        rho_dev = _chk(rho.reshape(1), (1,), torch.float64, 'rho')
+        rho = 0.0
+    assert counter.dtype == torch.int32 and counter.numel() == 1 and counter.is_cuda
+    if only_alpha:
+        pp = [ptr(prior[0].contiguous()), None, None, None, None]
+        tp = [ptr(theta[0]), None, None, None, None]
+    else:
+        for t in theta:
+            assert t.is_contiguous() and t.dtype == dt
+        pp = [ptr(t.contiguous()) for t in prior]
+        tp = [ptr(t) for t in theta]
+    _lib.call('vmp_suffstats_update', dt, N, K, D, ptr(x), ptr(r), int(bool(r_is_log)), ptr(u_nk), ptr(stats), ptr(counter),
+              float(rho), ptr(rho_dev), int(bool(only_alpha)), *pp, *tp, stream_ptr(dev), device=dev)
+    return stats
+
+
 def ng_update(stats, rho, prior, theta, only_alpha=False, want_star=False):
     """theta <- (1-rho) theta + rho (prior + stats terms), in place.  Returns theta* when want_star.
     rho: python float, or a 1-element float64 CUDA tensor (device-resident step size, CUDA-graph friendly)."""

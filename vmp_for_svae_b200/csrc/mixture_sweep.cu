@@ -19,6 +19,7 @@
 
 #include "block_linalg.cuh"
 #include "common.cuh"
+#include "ng_tail.cuh"
 
 namespace vmp {
 
@@ -130,22 +131,46 @@ sweep_prepare_kernel(int K, int D, int is_smm, const double* __restrict__ stats,
     chol_lower_block(C, D, ld);
     tri_inverse_block(C, W, D, ld);
     const double ak = (double)alpha_0[k] + Nk;
+    // the special functions are spread over the threads (each is a few hundred cycles of serial double arithmetic):
+    // thread i < D: log L_ii and psi((v [+1] + i) / 2); thread D .. D+3: psi(alpha_k), psi(sum alpha), the two lgammas
+    const double kap = is_smm ? (double)kappa_k[k] : 0.0;
+    double part = 0.0;
+    {
+        const int t = threadIdx.x;
+        if (t < D) {
+            const double psi = digamma_pos(0.5 * (vk + (is_smm ? 0.0 : 1.0) + t));            // gmm.py:128-129 / smm.py:108
+            part = 0.5 * psi + (is_smm ? -log(C[t * ld + t]) : 0.0);                           // 1/2 logdet P = -sum log Lc_ii
+            xk[t] = log(C[t * ld + t]);                                                        // (xk is free again) for the GMM guard
+        } else if (t == D) {
+            part = digamma_pos(ak);
+        } else if (t == D + 1) {
+            part = -digamma_pos(sa);
+        } else if (t == D + 2 && is_smm) {
+            part = lgamma(0.5 * (D + kap));
+        } else if (t == D + 3 && is_smm) {
+            part = -lgamma(0.5 * kap);
+        }
+    }
+    const double tot = block_sum(part, red);
+    __shared__ double tot_s, elogpi_s;
+    if (threadIdx.x == D) elogpi_s = part;
+    __syncthreads();
+    if (threadIdx.x == D + 1) elogpi_s += part;
+    if (threadIdx.x == 0) tot_s = tot;
+    __syncthreads();
+    const double elogpi = elogpi_s;
     double logdetC = 0.0;
-    for (int i = 0; i < D; ++i) logdetC += 2.0 * log(C[i * ld + i]);
+    for (int i = 0; i < D; ++i) logdetC += 2.0 * xk[i];
     const double logdetP = -logdetC;
-    const double elogpi = digamma_pos(ak) - digamma_pos(sa);
-    double sd = 0.0, c, hk, ek = 0.0, Dk = 0.0;
+    double c, hk, ek = 0.0, Dk = 0.0;
     const double dbeta = (double)D / bk;
     if (!is_smm) {
-        for (int i = 0; i < D; ++i) sd += digamma_pos(0.5 * (vk + 1.0 + i));                  // gmm.py:128-129
         const double ld_guard = (logdetP > -46.051701859880914) ? logdetP : 0.0;              // det > 1e-20 (gmm.py:120-121)
-        c = elogpi + 0.5 * (sd + D * VMP_LOG_2 + ld_guard);
+        c = tot_s + 0.5 * (D * VMP_LOG_2 + ld_guard);                                         // E log pi + 1/2 E log|Lambda|
         hk = 0.5;
     } else {
-        for (int i = 0; i < D; ++i) sd += digamma_pos(0.5 * (vk + i));                        // smm.py:108
-        const double kap = (double)kappa_k[k];
-        c = lgamma(0.5 * (D + kap)) - lgamma(0.5 * kap) - 0.5 * D * log(kap * 3.14159265358979323846) + elogpi +
-            0.5 * (sd + D * VMP_LOG_2 + logdetP) + log(kap);                                  // smm.py:119-124
+        // smm.py:119-124: lgamma((D+kap)/2) - lgamma(kap/2) - D/2 log(kap pi) + E log pi + 1/2 E log|Lambda| + log kap
+        c = tot_s + 0.5 * D * VMP_LOG_2 - 0.5 * D * log(kap * 3.14159265358979323846) + log(kap);
         hk = 0.5 * (D + kap);
         ek = dbeta + kap;
         Dk = D + kap;
@@ -263,6 +288,37 @@ __device__ __forceinline__ void sw_get_row(const float* xs, int p, float (&xt)[D
     xt[D] = 1.f;
 }
 
+// pair-interleaved tile for the packed e-step: element (p, i) at (p / 2) * 2D + 2 i + (p & 1), so that one 64-bit read yields
+// (x_{2q}[i], x_{2q+1}[i]) — the operand pair of an FFMA2 — without register shuffling.  Rows past `cnt` repeat row cnt-1.
+template <int D>
+__device__ __forceinline__ void sw_load_x_clamped(const float* __restrict__ x, int64_t n0, int cnt, float (&pre)[D], int lane) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const int e = lane + 32 * j, p = e / D, i = e - p * D;
+        pre[j] = x[(n0 + min(p, cnt - 1)) * D + i];
+    }
+}
+template <int D>
+__device__ __forceinline__ void sw_put_x_pairs(float* xs, const float (&pre)[D], int lane) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const int e = lane + 32 * j, p = e / D, i = e - p * D;
+        xs[(p >> 1) * 2 * D + 2 * i + (p & 1)] = pre[j];
+    }
+}
+template <int D>
+__device__ __forceinline__ void sw_get_pair(const float* xs, int q, float (&xa)[D + 1], float (&xb)[D + 1]) {
+    const float2* src = reinterpret_cast<const float2*>(xs + q * 2 * D);
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        const float2 v = src[i];
+        xa[i] = v.x;
+        xb[i] = v.y;
+    }
+    xa[D] = 1.f;
+    xb[D] = 1.f;
+}
+
 // ---------------------------------------------------------------------------------------------------- S: statistics of a given state
 // ASYNC: the r / u rows of 8 points at a time are staged through a per-warp 3-deep cp.async ring (16-byte copies: needs
 // K % 4 == 0 and 16-byte aligned r / u), so ~4 KB per warp are in flight while the previous group is accumulated; the plain
@@ -270,7 +326,7 @@ __device__ __forceinline__ void sw_get_row(const float* xs, int p, float (&xt)[D
 template <int D, bool ASYNC>
 __global__ void __launch_bounds__(SW_WARPS * 32, 2)
 sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ u,
-                   double* __restrict__ stats) {
+                   double* __restrict__ stats, const NgTail tail) {
     constexpr int NA = sw_na(D), GP = 8, NST = 3;
     __shared__ double red[NA + 1][32];
     __shared__ __align__(16) float xsm[SW_WARPS][32 * D];
@@ -355,6 +411,7 @@ sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
     if constexpr (ASYNC) sw_cp_wait<0>();
     __syncthreads();
     sw_store_stats<D>(red, K, u != nullptr, stats);
+    ng_tail_run<float>(tail, K, D, stats, gridDim.x);
 }
 
 // ---------------------------------------------------------------------------------------------------- E: e-step (+ next statistics)
@@ -392,23 +449,23 @@ sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
     for (int64_t run = gw; run * SW_RUN < N; run += nwarps) {
         const int64_t r0 = run * SW_RUN, r1 = min(N, r0 + SW_RUN);
         float pre[D];
-        sw_load_x<D>(x, r0, (int)min((int64_t)32, r1 - r0), pre, lane);
+        sw_load_x_clamped<D>(x, r0, (int)min((int64_t)32, r1 - r0), pre, lane);
         for (int64_t b0 = r0; b0 < r1; b0 += 32) {
+            // every batch is evaluated as 32 points (rows past the end repeat the last one): no data-dependent branch around
+            // the warp collectives; only the stores and the statistics weights are predicated
             const int cnt = (int)min((int64_t)32, r1 - b0);
             __syncwarp();
-            sw_put_x<D>(xs, pre, lane);
+            sw_put_x_pairs<D>(xs, pre, lane);
             __syncwarp();
-            if (b0 + 32 < r1) sw_load_x<D>(x, b0 + 32, (int)min((int64_t)32, r1 - b0 - 32), pre, lane);   // prefetch
+            if (b0 + 32 < r1) sw_load_x_clamped<D>(x, b0 + 32, (int)min((int64_t)32, r1 - b0 - 32), pre, lane);   // prefetch
 #pragma unroll 1
-            for (int p0 = 0; p0 < cnt; p0 += GP) {
+            for (int p0 = 0; p0 < 32; p0 += GP) {
                 // ---- scores of GP points: q = v (x - m)^T P (x - m) in triangular form, two points per packed FFMA2
                 float qv[GP];
 #pragma unroll
                 for (int pp = 0; pp < GP / 2; ++pp) {
-                    const int pa = min(p0 + 2 * pp, cnt - 1), pb = min(p0 + 2 * pp + 1, cnt - 1);     // clamped: tail rows repeat
                     float xa[D + 1], xb[D + 1], da[D], db[D];
-                    sw_get_row<D>(xs, pa, xa);
-                    sw_get_row<D>(xs, pb, xb);
+                    sw_get_pair<D>(xs, p0 / 2 + pp, xa, xb);
 #pragma unroll
                     for (int i = 0; i < D; ++i) sw_fadd2_bcast(da[i], db[i], xa[i], xb[i], rc[NP + i]);   // x - m (record holds -m)
                     float qa = 0.f, qb = 0.f;
@@ -438,22 +495,30 @@ sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
 #pragma unroll
                     for (int g = 0; g < GP; ++g) sv[g] += __shfl_xor_sync(0xffffffffu, sv[g], o);
                 }
+                float rr[GP], uu[GP];
 #pragma unroll
                 for (int g = 0; g < GP; ++g) {
-                    const int p = p0 + g;
-                    const float rr = __fdividef(ev[g], sv[g]);
-                    const float uu = SMM ? __fdividef(Dk, qv[g] + ek) : 1.f;                 // smm.py:131-137
-                    const bool live = p < cnt;
-                    if (WRITE && kin && live) {
-                        r[(b0 + p) * K + lane] = rr;
-                        if (SMM) u[(b0 + p) * K + lane] = uu;
+                    rr[g] = __fdividef(ev[g], sv[g]);
+                    uu[g] = SMM ? __fdividef(Dk, qv[g] + ek) : 1.f;                          // smm.py:131-137
+                }
+                if (WRITE && kin) {
+#pragma unroll
+                    for (int g = 0; g < GP; ++g) {
+                        if (p0 + g < cnt) {
+                            r[(b0 + p0 + g) * K + lane] = rr[g];
+                            if (SMM) u[(b0 + p0 + g) * K + lane] = uu[g];
+                        }
                     }
-                    if constexpr (STATS) {
-                        float xt[D + 1];
-                        sw_get_row<D>(xs, min(p, cnt - 1), xt);
-                        const float rl = live ? rr : 0.f;
-                        racc += rl;
-                        sw_accumulate<D>(acc, xt, rl * uu);
+                }
+                if constexpr (STATS) {
+#pragma unroll
+                    for (int pp = 0; pp < GP / 2; ++pp) {
+                        float xa[D + 1], xb[D + 1];
+                        sw_get_pair<D>(xs, p0 / 2 + pp, xa, xb);
+                        const float ra = p0 + 2 * pp < cnt ? rr[2 * pp] : 0.f, rb = p0 + 2 * pp + 1 < cnt ? rr[2 * pp + 1] : 0.f;
+                        racc += ra + rb;
+                        sw_accumulate<D>(acc, xa, ra * uu[2 * pp]);
+                        sw_accumulate<D>(acc, xb, rb * uu[2 * pp + 1]);
                     }
                 }
             }
@@ -480,17 +545,18 @@ static int sw_grid(const void* kern, int64_t N, int warps, size_t dyn_smem = 0) 
 }
 
 template <int D>
-static int sw_launch_stats(int64_t N, int K, const float* x, const float* r, const float* u, double* stats, cudaStream_t st) {
+static int sw_launch_stats(int64_t N, int K, const float* x, const float* r, const float* u, double* stats, const NgTail& tail,
+                           cudaStream_t st) {
     const bool aligned = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(u)) % 16 == 0);
     if (aligned) {
         auto kern = sweep_stats_kernel<D, true>;
         constexpr int ring_bytes = SW_WARPS * 3 * 2 * 8 * 32 * (int)sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);
         if (e != cudaSuccess) return (int)e;
-        kern<<<sw_grid((const void*)kern, N, SW_WARPS, ring_bytes), SW_WARPS * 32, ring_bytes, st>>>(N, K, x, r, u, stats);
+        kern<<<sw_grid((const void*)kern, N, SW_WARPS, ring_bytes), SW_WARPS * 32, ring_bytes, st>>>(N, K, x, r, u, stats, tail);
     } else {
         auto kern = sweep_stats_kernel<D, false>;
-        kern<<<sw_grid((const void*)kern, N, SW_WARPS), SW_WARPS * 32, 0, st>>>(N, K, x, r, u, stats);
+        kern<<<sw_grid((const void*)kern, N, SW_WARPS), SW_WARPS * 32, 0, st>>>(N, K, x, r, u, stats, tail);
     }
     return launch_status();
 }
@@ -592,10 +658,10 @@ int mixture_fit(int64_t N, int K, int D, int is_smm, int n_sweeps, const T* x, c
 // sweep's statistics or nullptr; write = store r / u)
 template <> struct SweepFast<float> {
     static int run(int64_t N, int K, int D, int mode, const float* x, const float* rec, float* r, float* u, double* stats_in,
-                   double* stats_out, int, bool write, cudaStream_t st) {
+                   double* stats_out, int, bool write, cudaStream_t st, const NgTail& tail = ng_tail_none()) {
 #define VMP_SW_CASE(DD)                                                                              \
     case DD:                                                                                         \
-        if (mode == 0) return sw_launch_stats<DD>(N, K, x, r, u, stats_in, st);                      \
+        if (mode == 0) return sw_launch_stats<DD>(N, K, x, r, u, stats_in, tail, st);                \
         if (mode == 1) return sw_launch_estep<DD, false>(N, K, x, rec, r, u, stats_out, write, st);  \
         return sw_launch_estep<DD, true>(N, K, x, rec, r, u, stats_out, write, st);
         switch (D) {
@@ -628,9 +694,11 @@ int mixture_prepare(int K, int D, int is_smm, const double* stats, double* stats
 }
 
 // fp32 D <= 8 K <= 32 statistics of a given state (called from vmp_suffstats_f32 for these shapes)
-int sweep_stats_f32(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, cudaStream_t st) {
+int sweep_stats_f32(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, const NgTail& tail,
+                    cudaStream_t st) {
     if (D > 8 || K > 32) return -100;
-    return SweepFast<float>::run(N, K, D, 0, x, nullptr, const_cast<float*>(r), const_cast<float*>(u), stats, nullptr, 0, false, st);
+    return SweepFast<float>::run(N, K, D, 0, x, nullptr, const_cast<float*>(r), const_cast<float*>(u), stats, nullptr, 0, false, st,
+                                 tail);
 }
 
 }  // namespace vmp

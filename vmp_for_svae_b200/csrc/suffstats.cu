@@ -9,6 +9,7 @@
 // points (two-level summation keeps the fp32 rounding at the 1e-6 level for any N), and finally one double
 // atomicAdd per output per CTA.
 #include "common.cuh"
+#include "ng_tail.cuh"
 
 
 namespace vmp {
@@ -43,7 +44,8 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 template <typename T>
 __global__ void __launch_bounds__(320)
 suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per_slice, const T* __restrict__ x,
-                 const T* __restrict__ r, int r_is_log, const T* __restrict__ u_nk, double* __restrict__ stats) {
+                 const T* __restrict__ r, int r_is_log, const T* __restrict__ u_nk, double* __restrict__ stats,
+                 const NgTail tail) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int KC = SS_KT * G;                       // components covered by this CTA
     T* xs0 = reinterpret_cast<T*>(smraw);           // [2][SS_CH][D4]   xt = [x, 1, 0 pad]
@@ -174,7 +176,7 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
         }
         __syncthreads();      // everyone is done with this buffer before the next-but-one prefetch overwrites it
     }
-    if (!active) return;
+    if (active) {
     const int SL = stats_len(D);
 #pragma unroll
     for (int q = 0; q < SS_KT; ++q) {
@@ -201,6 +203,8 @@ suffstats_kernel(int64_t N, int K, int D, int D4, int nb, int G, int64_t pts_per
             }
         if (u_nk != nullptr && b == 0) atomicAdd(out + 0, dracc[q]);
     }
+    }
+    ng_tail_run<T>(tail, K, D, stats, gridDim.x * gridDim.y);
 }
 
 // ---- small latent dimension (D <= 8: the C1-C3 shapes): lane <-> component --------------------------------------
@@ -213,7 +217,7 @@ constexpr int SSM_WARPS = 8;
 template <typename T, int D>
 __global__ void __launch_bounds__(SSM_WARPS * 32)
 suffstats_small_kernel(int64_t N, int K, const T* __restrict__ x, const T* __restrict__ r, int r_is_log,
-                       const T* __restrict__ u_nk, double* __restrict__ stats, int64_t pts_per_warp) {
+                       const T* __restrict__ u_nk, double* __restrict__ stats, int64_t pts_per_warp, const NgTail tail) {
     constexpr int NA = (D + 1) * (D + 2) / 2;
     __shared__ double red[NA + 1][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -276,11 +280,12 @@ suffstats_small_kernel(int64_t N, int K, const T* __restrict__ x, const T* __res
             atomicAdd(out + 1, v);
         }
     }
+    ng_tail_run<T>(tail, K, D, stats, gridDim.x * gridDim.y);
 }
 
 template <typename T, int D>
 static int launch_suffstats_small(int64_t N, int K, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
-                                  cudaStream_t st) {
+                                  const NgTail& tail, cudaStream_t st) {
     const int kblocks = (K + 31) / 32;
     int64_t ppw = SSM_RUN;
     const int64_t want_ctas = 148 * 2;
@@ -289,43 +294,45 @@ static int launch_suffstats_small(int64_t N, int K, const T* x, const T* r, int 
     const int64_t grid = (N + ppw * SSM_WARPS - 1) / (ppw * SSM_WARPS);
     if (grid > 0x7fffffffLL) return VMP_E_BADARG;
     suffstats_small_kernel<T, D><<<dim3((unsigned)grid, kblocks), SSM_WARPS * 32, 0, st>>>(N, K, x, r, r_is_log, u_nk,
-                                                                                          stats, ppw);
+                                                                                          stats, ppw, tail);
     return launch_status();
 }
 
 // tensor-core contraction (suffstats_tc.cu): fp32, D = 64, even K, GMM weights, N >= 128
-int suffstats_tc(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, double* stats, cudaStream_t st);
+int suffstats_tc(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, double* stats, const NgTail& tail,
+                 cudaStream_t st);
 template <typename T>
-static int suffstats_tc_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, cudaStream_t) { return -100; }
+static int suffstats_tc_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, const NgTail&, cudaStream_t) { return -100; }
 template <>
 int suffstats_tc_dispatch<float>(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
-                                 double* stats, cudaStream_t st) {
+                                 double* stats, const NgTail& tail, cudaStream_t st) {
     if (u_nk != nullptr) return -100;
-    return suffstats_tc(N, K, D, x, r, r_is_log, stats, st);
+    return suffstats_tc(N, K, D, x, r, r_is_log, stats, tail, st);
 }
 
 // fp32, D <= 8, K <= 32, plain responsibilities: the lane <-> component kernel of mixture_sweep.cu
-int sweep_stats_f32(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, cudaStream_t st);
+int sweep_stats_f32(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, const NgTail& tail,
+                    cudaStream_t st);
 template <typename T>
-static int sweep_stats_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, cudaStream_t) { return -100; }
+static int sweep_stats_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, const NgTail&, cudaStream_t) { return -100; }
 template <>
 int sweep_stats_dispatch<float>(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
-                                double* stats, cudaStream_t st) {
+                                double* stats, const NgTail& tail, cudaStream_t st) {
     if (r_is_log || D > 8 || K > 32) return -100;
-    return sweep_stats_f32(N, K, D, x, r, u_nk, stats, st);
+    return sweep_stats_f32(N, K, D, x, r, u_nk, stats, tail, st);
 }
 
 template <typename T>
 int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, const T* u_nk, double* stats,
-              void* stream) {
+              const NgTail& tail, void* stream) {
     if (N < 0 || K <= 0) return VMP_E_BADARG;
     if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
     if (N == 0) return VMP_OK;
     if (!x || !r || !stats) return VMP_E_BADARG;
-    if (int rc = sweep_stats_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream); rc != -100) return rc;
-    if (int rc = suffstats_tc_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream); rc != -100) return rc;
+    if (int rc = sweep_stats_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, tail, (cudaStream_t)stream); rc != -100) return rc;
+    if (int rc = suffstats_tc_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, tail, (cudaStream_t)stream); rc != -100) return rc;
 #define VMP_SSM(DD) \
-    case DD: return launch_suffstats_small<T, DD>(N, K, x, r, r_is_log, u_nk, stats, (cudaStream_t)stream)
+    case DD: return launch_suffstats_small<T, DD>(N, K, x, r, r_is_log, u_nk, stats, tail, (cudaStream_t)stream)
     switch (D) {
         VMP_SSM(1); VMP_SSM(2); VMP_SSM(3); VMP_SSM(4); VMP_SSM(5); VMP_SSM(6); VMP_SSM(7); VMP_SSM(8);
         default: break;
@@ -355,7 +362,7 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
         if (e != cudaSuccess) return (int)e;
     }
     kern<<<dim3(ktiles, nslices), threads, smem, (cudaStream_t)stream>>>(N, K, D, D4, nb, G, pps, x, r, r_is_log, u_nk,
-                                                                        stats);
+                                                                        stats, tail);
     return launch_status();
 }
 
@@ -467,11 +474,41 @@ int mixture_mstep(int K, int D, int is_smm, const double* stats, const T* alpha_
 extern "C" {
 int vmp_suffstats_f32(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
                       double* stats, void* stream) {
-    return vmp::suffstats<float>(N, K, D, x, r, r_is_log, u_nk, stats, stream);
+    return vmp::suffstats<float>(N, K, D, x, r, r_is_log, u_nk, stats, vmp::ng_tail_none(), stream);
 }
 int vmp_suffstats_f64(int64_t N, int K, int D, const double* x, const double* r, int r_is_log, const double* u_nk,
                       double* stats, void* stream) {
-    return vmp::suffstats<double>(N, K, D, x, r, r_is_log, u_nk, stats, stream);
+    return vmp::suffstats<double>(N, K, D, x, r, r_is_log, u_nk, stats, vmp::ng_tail_none(), stream);
+}
+static vmp::NgTail make_tail(unsigned int* counter, double rho, const double* rho_dev, int only_alpha, const void* p_alpha,
+                             const void* p_A, const void* p_b, const void* p_beta, const void* p_vhat, void* alpha, void* A,
+                             void* b, void* beta, void* v_hat) {
+    vmp::NgTail t;
+    t.counter = counter; t.rho = rho; t.rho_dev = rho_dev; t.only_alpha = only_alpha;
+    t.p_alpha = p_alpha; t.p_A = p_A; t.p_b = p_b; t.p_beta = p_beta; t.p_vhat = p_vhat;
+    t.alpha = alpha; t.A = A; t.b = b; t.beta = beta; t.v_hat = v_hat;
+    return t;
+}
+static bool tail_ok(const vmp::NgTail& t) {
+    if (!t.counter || !t.p_alpha || !t.alpha) return false;
+    return t.only_alpha || (t.p_A && t.p_b && t.p_beta && t.p_vhat && t.A && t.b && t.beta && t.v_hat);
+}
+int vmp_suffstats_update_f32(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
+                             double* stats, unsigned int* counter, double rho, const double* rho_dev, int only_alpha,
+                             const float* p_alpha, const float* p_A, const float* p_b, const float* p_beta,
+                             const float* p_vhat, float* alpha, float* A, float* b, float* beta, float* v_hat, void* stream) {
+    const vmp::NgTail t = make_tail(counter, rho, rho_dev, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta, v_hat);
+    if (N <= 0 || !tail_ok(t)) return VMP_E_BADARG;
+    return vmp::suffstats<float>(N, K, D, x, r, r_is_log, u_nk, stats, t, stream);
+}
+int vmp_suffstats_update_f64(int64_t N, int K, int D, const double* x, const double* r, int r_is_log, const double* u_nk,
+                             double* stats, unsigned int* counter, double rho, const double* rho_dev, int only_alpha,
+                             const double* p_alpha, const double* p_A, const double* p_b, const double* p_beta,
+                             const double* p_vhat, double* alpha, double* A, double* b, double* beta, double* v_hat,
+                             void* stream) {
+    const vmp::NgTail t = make_tail(counter, rho, rho_dev, only_alpha, p_alpha, p_A, p_b, p_beta, p_vhat, alpha, A, b, beta, v_hat);
+    if (N <= 0 || !tail_ok(t)) return VMP_E_BADARG;
+    return vmp::suffstats<double>(N, K, D, x, r, r_is_log, u_nk, stats, t, stream);
 }
 int vmp_ng_update_f32(int K, int D, const double* stats, double rho, const double* rho_dev, int only_alpha,
                       const float* p_alpha,

@@ -21,6 +21,7 @@
 //   offset(row j, point n) = (j/8) * 1024 + (n/4) * 128 + (j%8) * 16 + (n%4) * 4 bytes   (LBO = 128 B, SBO = 1024 B).
 // TMEM accumulator layout (measured): M = 128 puts row m in lane m; M = 64 would use lanes 32 * (i / 16) + i % 16.
 #include "common.cuh"
+#include "ng_tail.cuh"
 
 namespace vmp {
 
@@ -72,7 +73,7 @@ __device__ __forceinline__ void tc_bar_arrive(int id, int count) { asm volatile(
 // TMEM lane m holds row m % 64 of component k0 + m / 64.
 __global__ void __launch_bounds__(TC_THREADS + 32, 1)
 suffstats_tc_kernel(int64_t N, int K, int64_t pts_per_slice, const float* __restrict__ x, const float* __restrict__ r,
-                    int r_is_log, double* __restrict__ stats) {
+                    int r_is_log, double* __restrict__ stats, const NgTail tail) {
     extern __shared__ __align__(1024) unsigned char smraw[];
     float* tiles = reinterpret_cast<float*>(smraw);                       // [2][6][TC_TILE]: Ahi (2 tiles) Alo (2) Bhi Blo
     float* raw = tiles + 2 * 6 * TC_TILE;                                 // [2][TC_PC][TC_RAWLD]
@@ -87,7 +88,10 @@ suffstats_tc_kernel(int64_t N, int K, int64_t pts_per_slice, const float* __rest
     const int k0 = 2 * blockIdx.x;
     const int64_t n_begin = (int64_t)blockIdx.y * pts_per_slice;
     const int64_t n_end = min(N, n_begin + pts_per_slice);
-    if (n_begin >= n_end) return;
+    if (n_begin >= n_end) {
+        ng_tail_run<float>(tail, K, TC_D, stats, gridDim.x * gridDim.y);
+        return;
+    }
     const int nchunks = (int)((n_end - n_begin + TC_PC - 1) / TC_PC);
 
     for (int e = tid; e < 2 * TC_D * TC_DLD + 2 * (TC_D + 2); e += TC_THREADS + 32) dacc[e] = 0.0;   // dacc | dsum contiguous
@@ -279,6 +283,7 @@ suffstats_tc_kernel(int64_t N, int K, int64_t pts_per_slice, const float* __rest
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(taddr) : "memory");
+    ng_tail_run<float>(tail, K, TC_D, stats, gridDim.x * gridDim.y);
 }
 
 size_t suffstats_tc_smem_bytes() {
@@ -287,7 +292,8 @@ size_t suffstats_tc_smem_bytes() {
 }
 
 // returns VMP_OK, a CUDA error, or -100 when the shape does not qualify (caller falls back to the FP32 kernels)
-int suffstats_tc(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, double* stats, cudaStream_t st) {
+int suffstats_tc(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, double* stats, const NgTail& tail,
+                 cudaStream_t st) {
     if (D != TC_D || (K & 1) || N < 4 * TC_PC) return -100;
     const size_t smem = suffstats_tc_smem_bytes();
     cudaError_t e = cudaFuncSetAttribute(suffstats_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -300,7 +306,7 @@ int suffstats_tc(int64_t N, int K, int D, const float* x, const float* r, int r_
     int64_t pps = (N + nslices - 1) / nslices;
     pps = ((pps + TC_PC - 1) / TC_PC) * TC_PC;
     nslices = (int)((N + pps - 1) / pps);
-    suffstats_tc_kernel<<<dim3(kpairs, nslices), TC_THREADS + 32, smem, st>>>(N, K, pps, x, r, r_is_log, stats);
+    suffstats_tc_kernel<<<dim3(kpairs, nslices), TC_THREADS + 32, smem, st>>>(N, K, pps, x, r, r_is_log, stats, tail);
     return launch_status();
 }
 

@@ -6,6 +6,7 @@ natural-gradient update (experiments.py:208-260 in one allocation-free sequence 
     suffstats                   [N_k, sum r x, sum r x x^T] of this shard, double
     all-reduce (NCCL)           the packed K*(D^2+D+2)+4 doubles — the only exchange of the step
     ng_update                   theta <- (1-rho) theta + rho (prior + stats)   (identical on every rank)
+On one GPU the last two lines disappear: the update runs in the tail of the statistics kernel (vmp_suffstats_update).
 
 Points are sharded contiguously across ranks, phi_gmm / theta / prior are replicated.  The ELBO is evaluated with
 theta BEFORE the update (the reference leaves the order undefined; the oracle fixes the same order).
@@ -39,7 +40,7 @@ class SVAEStep(object):
             use_dist = torch.distributed.is_available() and torch.distributed.is_initialized() and \
                 torch.distributed.get_world_size(process_group) > 1
         self.use_dist = bool(use_dist)
-        self.launches_per_step = 7      # phi, theta, local_step, select_sample, suffstats, ng_update (+ memset)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)   # ticket counter of the fused NG tail
 
     def step(self, phi_enc, phi_gmm, theta, prior, rho, seed=0, noise=None, u=None, only_alpha=False,
              kernel_events=None):
@@ -59,13 +60,18 @@ class SVAEStep(object):
                         workspace=self.workspace, point_offset=self.point_offset)
         if kernel_events is not None:
             kernel_events[1].record()
-        core.suffstats(self.x_sample, self.log_r, r_is_log=True, stats=self.stats)
-        if self.use_dist:
-            torch.distributed.all_reduce(self.red, group=self.pg)
-        if only_alpha:
-            core.ng_update(self.stats, rho, [prior[0]], [theta[0]], only_alpha=True)
+        if not self.use_dist:
+            # single GPU: the natural-gradient update rides in the tail of the statistics reduction (one launch)
+            core.suffstats_update(self.x_sample, self.log_r, self.stats, self.counter, rho,
+                                  [prior[0]] if only_alpha else prior, [theta[0]] if only_alpha else theta, r_is_log=True,
+                                  only_alpha=only_alpha)
         else:
-            core.ng_update(self.stats, rho, prior, theta)
+            core.suffstats(self.x_sample, self.log_r, r_is_log=True, stats=self.stats)
+            torch.distributed.all_reduce(self.red, group=self.pg)
+            if only_alpha:
+                core.ng_update(self.stats, rho, [prior[0]], [theta[0]], only_alpha=True)
+            else:
+                core.ng_update(self.stats, rho, prior, theta)
         return dict(log_r=self.log_r, x_sample=self.x_sample, z=self.z, elbo_acc=self.elbo_acc)
 
 
