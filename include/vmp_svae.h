@@ -105,6 +105,29 @@ int vmp_svae_local_step_f64(int64_t N, int K, int D, int S, const double* eta1, 
  * samples (x_in) the thread-per-pair kernels run instead.  No environment variable selects anything.     */
 size_t vmp_svae_local_step_workspace_bytes(int K, int D);
 
+/* ---- the whole step in one launch (launch-bound configurations: BASELINE C1 / C2) --------------------------------------
+ * phi / theta prologues + local step + selection + statistics + natural-gradient update as ONE kernel on one thread-block
+ * cluster (csrc/small_step.cu); replaces the same reference lines as vmp_phi_prepare + vmp_theta_prepare_* +
+ * vmp_svae_local_step + vmp_suffstats + vmp_ng_update (svae.py:14-176, 199-322, 342-403).  Single GPU; D <= 8, K <= 32,
+ * N*K <= 8192 (vmp_svae_small_step_supported).  theta / prior / theta_out are HOST arrays of device pointers:
+ *   den_mode VMP_DEN_GAUSS   : theta = {alpha, A, b, beta, v_hat}; VMP_DEN_STUDENT: theta = {alpha, mu, L_raw, dof}
+ *   prior = {alpha, A, b, beta, v_hat} (only prior[0] when only_alpha); theta_out = the tensors updated in place
+ *   (theta itself for the GMM; {alpha} with only_alpha != 0 for the SMM, svae.m_step_smm 179-196).
+ * stats[K, vmp_stats_len(D)] and elbo_acc[4] are OVERWRITTEN (not accumulated).  Other arguments as vmp_svae_local_step_*.  */
+int vmp_svae_small_step_supported(int64_t N, int K, int D);
+int vmp_svae_small_step_f32(int64_t N, int K, int D, int S, int den_mode, int only_alpha, const float* eta1,
+                            const float* eta2_diag, const float* eta1_phi2, const float* L_raw, const float* pi_raw,
+                            const float* const* theta, const float* const* prior, float* const* theta_out, double rho,
+                            const double* rho_dev, const float* noise, const float* gumbel_u, uint64_t seed,
+                            int64_t point_offset, float* log_r, float* x_sample, int32_t* z, float* x_k_samples, double* stats,
+                            double* elbo_acc, void* stream);
+int vmp_svae_small_step_f64(int64_t N, int K, int D, int S, int den_mode, int only_alpha, const double* eta1,
+                            const double* eta2_diag, const double* eta1_phi2, const double* L_raw, const double* pi_raw,
+                            const double* const* theta, const double* const* prior, double* const* theta_out, double rho,
+                            const double* rho_dev, const double* noise, const double* gumbel_u, uint64_t seed,
+                            int64_t point_offset, double* log_r, double* x_sample, int32_t* z, double* x_k_samples,
+                            double* stats, double* elbo_acc, void* stream);
+
 /* ---- reverse pass of the fused local step ---------------------------------------------------------------
  * Replaces what TF's autodiff builds for opt.compute_gradients(-elbo) (experiments.py:232) through svae.e_step
  * (svae.py:39-100), the per-component sampling (svae.py:103-123) and the regulariser of compute_elbo / compute_elbo_smm

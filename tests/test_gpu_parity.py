@@ -697,6 +697,51 @@ def test_fused_statistics_update_equals_two_launches(shape, dt, only_alpha):
             torch.testing.assert_close(b, a, rtol=1e-6 if dt == torch.float32 else 1e-12, atol=1e-7)
 
 
+@pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
+@pytest.mark.parametrize('shape', [(100, 10, 2, 10), (274, 10, 6, 10), (255, 32, 8, 2), (1, 3, 4, 1), (130, 1, 5, 2), (37, 7, 1, 3),
+                                   (700, 11, 3, 1)], ids=lambda s: 'N%dK%dD%dS%d' % s)
+@pytest.mark.parametrize('student', [False, True], ids=['gauss', 'student'])
+def test_single_launch_step_equals_multi_launch(shape, dt, student):
+    """csrc/small_step.cu (prologues + local step + selection + statistics + natural-gradient update in ONE cluster kernel, what
+    SVAEStep runs for C1 / C2 on one GPU) == the multi-launch sequence, on in-kernel noise and on injected noise."""
+    from vmp_for_svae_b200 import core
+    from vmp_for_svae_b200.step import SVAEStep
+    N, K, D, S = shape
+    prior, theta, phi_gmm, phi_enc, noise, u = _oracle_inputs(N, K, D, S, seed=N + D, spread=0.3)
+    dev = lambda ts: [t.to(device=DEV, dtype=dt).contiguous() for t in ts]
+    pe, pg, pr = dev(phi_enc), dev(phi_gmm), dev(prior)
+    rs = np.random.RandomState(3)
+    if student:
+        mk = lambda: [dev(theta)[0], T(rs.randn(K, D)).to(DEV, dt), (T(0.3 / D ** 0.5 * np.random.RandomState(5).randn(K, D, D)) +
+                      torch.eye(D, dtype=torch.float64)).to(DEV, dt).contiguous(), T(3.0 + 5.0 * np.random.RandomState(6).rand(K)).to(DEV, dt)]
+        rs = np.random.RandomState(3); th_a = mk(); rs = np.random.RandomState(3); th_b = mk()
+        kw = dict(den_mode=core.DEN_STUDENT)
+    else:
+        th_a, th_b, kw = dev(theta), dev(theta), {}
+    for call in (dict(seed=11), dict(noise=noise.to(DEV, dt).contiguous(), u=u.to(DEV, dt).contiguous())):
+        one = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False, point_offset=77, **kw)
+        multi = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False, point_offset=77, **kw)
+        assert one.single_launch
+        multi.single_launch = False
+        oa = one.step(pe, pg, th_a, pr, 0.25, only_alpha=student, **call)
+        ob = multi.step(pe, pg, th_b, pr, 0.25, only_alpha=student, **call)
+        torch.cuda.synchronize()
+        rt = 1e-11 if dt == torch.float64 else 2e-5
+        ctx = dict(shape=list(shape), dtype=str(dt), student=student, injected='noise' in call)
+        check('one-launch log_r', torch.exp(oa['log_r']), torch.exp(ob['log_r']), rt, 1e-3, **ctx)
+        agree = (oa['z'] == ob['z']).double().mean().item()
+        assert agree >= (1.0 if dt == torch.float64 else 0.99)
+        m = oa['z'] == ob['z']
+        check('one-launch x_sample', oa['x_sample'][m], ob['x_sample'][m], rt, 1.0, **ctx)
+        scale = max(float(ob['elbo_acc'][:2].abs().max()), 1.0)
+        check('one-launch elbo', oa['elbo_acc'][:3], ob['elbo_acc'][:3], rt, scale, **ctx)
+        assert float(oa['elbo_acc'][3]) == 0.0
+        if agree == 1.0:
+            check('one-launch stats', one.stats, multi.stats, rt * 5, max(float(multi.stats.abs().max()), 1.0), **ctx)
+            for a, b in zip(th_a, th_b):
+                check('one-launch theta', a, b, rt * 5, max(float(b.abs().max()), 1.0), **ctx)
+
+
 def test_graphed_step_matches_eager_statistics():
     """SVAEStep.make_graph: replays move theta exactly like eager steps fed the same (graph-drawn) noise cannot be
     compared draw by draw, so check the invariants: N_k sums to N, theta stays finite and moves toward the statistics,

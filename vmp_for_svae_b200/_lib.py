@@ -20,6 +20,8 @@ _SIGS_T = {
     'vmp_theta_prepare_student': [c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr],
     'vmp_svae_local_step': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr, c_ptr, c_u64, c_i64,
                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr],
+    'vmp_svae_small_step': [c_i64, c_int, c_int, c_int, c_int, c_int] + [c_ptr] * 8 + [c_dbl, c_ptr, c_ptr, c_ptr, c_u64, c_i64] +
+                           [c_ptr] * 6 + [c_ptr],
     'vmp_svae_local_step_bwd': [c_i64, c_int, c_int, c_int] + [c_ptr] * 7 + [c_int, c_ptr, c_u64, c_ptr, c_ptr, c_ptr,
                                                                                c_dbl, c_ptr] + [c_ptr] * 6 +
                                [c_ptr, ctypes.c_size_t, c_ptr],
@@ -48,6 +50,7 @@ _SIGS = {
     'vmp_svae_local_step_bwd_workspace_bytes': [c_int, c_int],
     'vmp_mixture_fit_workspace_bytes': [c_int, c_int],
     'vmp_mixture_record_len': [c_int],
+    'vmp_svae_small_step_supported': [c_i64, c_int, c_int],
     'vmp_mixture_estep_fused_f32': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
     'vmp_fma_probe': [c_int, c_int, c_int, c_ptr, c_ptr],
 }

@@ -103,6 +103,55 @@ def local_step(eta1, eta2_diag, phi_rec, theta_rec, S, den_mode=DEN_GAUSS, noise
     return dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=x_k, elbo_acc=elbo_acc)
 
 
+def small_step_supported(N, K, D):
+    return bool(_lib.load().vmp_svae_small_step_supported(int(N), int(K), int(D)))
+
+
+def _ptr_array(tensors, n):
+    import ctypes
+    arr = (ctypes.c_void_p * n)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
+def small_step(eta1, eta2_diag, phi_gmm, theta, prior, theta_out, rho, S, den_mode=DEN_GAUSS, only_alpha=False, noise=None,
+               u=None, seed=0, point_offset=0, log_r=None, x_sample=None, z=None, stats=None, elbo_acc=None,
+               materialize_x_k=False):
+    """The whole step in ONE launch (vmp_svae_small_step; D <= 8, K <= 32, N*K <= 8192, single GPU): prologues, local step,
+    selection, statistics and the natural-gradient update of `theta_out` in place.  stats / elbo_acc are overwritten.
+    Returns dict(log_r, x_sample, z, x_k_samples, elbo_acc, stats)."""
+    N, D = eta1.shape
+    K = phi_gmm[0].shape[0]
+    dt, dev = eta1.dtype, eta1.device
+    eta1 = _chk(eta1, (N, D), dt, 'eta1'); eta2_diag = _chk(eta2_diag, (N, D), dt, 'eta2_diag')
+    e1, Lr, pr = (_chk(phi_gmm[0], (K, D), dt, 'eta1_phi2'), _chk(phi_gmm[1], (K, D, D), dt, 'L_k_raw'),
+                  _chk(phi_gmm[2], (K,), dt, 'pi_k_raw'))
+    for t in list(theta) + list(prior) + list(theta_out):
+        assert t.is_cuda and t.is_contiguous() and t.dtype == dt, 'theta / prior tensors must be contiguous CUDA tensors'
+    if noise is not None:
+        noise = _chk(noise, (N, K, D, S), dt, 'noise')
+    if u is not None:
+        u = _chk(u, (N, K), dt, 'u (gumbel uniforms)')
+    slen = _lib.record_lens(D)[2]
+    log_r = log_r if log_r is not None else torch.empty(N, K, dtype=dt, device=dev)
+    x_sample = x_sample if x_sample is not None else torch.empty(N, D, dtype=dt, device=dev)
+    z = z if z is not None else torch.empty(N, dtype=torch.int32, device=dev)
+    stats = stats if stats is not None else torch.empty(K, slen, dtype=torch.float64, device=dev)
+    elbo_acc = elbo_acc if elbo_acc is not None else torch.empty(4, dtype=torch.float64, device=dev)
+    x_k = torch.empty(N, K, S, D, dtype=dt, device=dev) if materialize_x_k else None
+    rho_dev = None
+    if isinstance(rho, torch.Tensor):
+        rho_dev = _chk(rho.reshape(1), (1,), torch.float64, 'rho')
+        rho = 0.0
+    th, pa, to = _ptr_array(theta, 5), _ptr_array(prior, 5), _ptr_array(theta_out, 5)
+    _lib.call('vmp_svae_small_step', dt, N, K, D, int(S), int(den_mode), int(bool(only_alpha)), ptr(eta1), ptr(eta2_diag),
+              ptr(e1), ptr(Lr), ptr(pr), th, pa, to, float(rho), ptr(rho_dev), ptr(noise), ptr(u),
+              int(seed) & 0xFFFFFFFFFFFFFFFF, int(point_offset), ptr(log_r), ptr(x_sample), ptr(z), ptr(x_k), ptr(stats),
+              ptr(elbo_acc), stream_ptr(dev), device=dev)
+    return dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=x_k, elbo_acc=elbo_acc, stats=stats)
+
+
 def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, S, log_r, gx, glr, greg,
                         den_mode=DEN_GAUSS, noise=None, seed=0, want_theta_rec_bar=False):
     """Reverse pass of the fused local step (vmp_svae_local_step_bwd): gradients of

@@ -41,12 +41,19 @@ class SVAEStep(object):
                 torch.distributed.get_world_size(process_group) > 1
         self.use_dist = bool(use_dist)
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)   # ticket counter of the fused NG tail
+        # launch-bound shapes on one GPU (C1 / C2): the whole step is ONE kernel on a thread-block cluster
+        self.single_launch = (not self.use_dist) and core.small_step_supported(self.N, K, D)
 
     def step(self, phi_enc, phi_gmm, theta, prior, rho, seed=0, noise=None, u=None, only_alpha=False,
              kernel_events=None):
         """Runs one step; mutates `theta` in place; returns dict(log_r, x_sample, z, elbo_acc) (device tensors,
         valid on the current stream).  elbo_acc = [sum r*num, sum r*den, regulariser, #bad pivots] over ALL ranks."""
         eta1, eta2_diag = phi_enc
+        if self.single_launch and kernel_events is None:
+            return core.small_step(eta1, eta2_diag, phi_gmm, theta, [prior[0]] if only_alpha else prior,
+                                   [theta[0]] if only_alpha else theta, rho, self.S, den_mode=self.den_mode,
+                                   only_alpha=only_alpha, noise=noise, u=u, seed=seed, point_offset=self.point_offset,
+                                   log_r=self.log_r, x_sample=self.x_sample, z=self.z, stats=self.stats, elbo_acc=self.elbo_acc)
         core.phi_prepare(phi_gmm[0], phi_gmm[1], phi_gmm[2], out=self.phi_rec)
         if self.den_mode == core.DEN_GAUSS:
             core.theta_prepare_gauss(theta, out=self.theta_rec)
