@@ -31,7 +31,7 @@ constexpr int SM_MAX_PAIRS_PER_CTA = 1024;
 constexpr int SM_MAX_K = 32;
 
 template <typename T> struct SmallStepParams {
-    int N, K, S, den_mode, only_alpha, ppc;      // ppc: points per CTA
+    int N, K, S, den_mode, only_alpha, ppc, split;   // ppc: points per CTA; split: threads sharing the S samples of a pair
     const T *eta1, *eta2d;
     const T *eta1_phi2, *L_raw, *pi_raw;          // phi_gmm
     const T *th0, *th1, *th2, *th3, *th4;         // theta: (alpha, A, b, beta, v_hat) or (alpha, mu, L_raw, dof, -)
@@ -224,24 +224,28 @@ __global__ void __launch_bounds__(SM_THREADS) svae_small_step_kernel(const Small
         else small_theta_record_student<T, D>(k, K, p.th0, p.th1, p.th2, p.th3, trec + (size_t)k * TL);
     }
     for (int e = tid; e < K * SL + 4; e += blockDim.x) sstat[e] = 0.0;
-    __syncthreads();
-
-    // ---------------- phase 1: pairs
     const int pt0 = crank * ppc;
     const int npts = max(0, min(ppc, p.N - pt0));
     const int npairs = npts * K;
+    for (int e = tid; e < npairs; e += blockDim.x) { tnum[e] = T(0); tden[e] = T(0); }
+    __syncthreads();
+
+    // ---------------- phase 1: pairs; `split` threads share the S samples of a pair (each refactors the tiny system: cheaper
+    // than waiting for one thread to walk through all samples)
+    const int split = p.split;
     int nbad = 0;
-    for (int q = tid; q < npairs; q += blockDim.x) {
+    for (int it = tid; it < npairs * split; it += blockDim.x) {
+        const int q = it / split, sp = it - q * split;
         const int pl = q / K, k = q - pl * K;
         const int64_t n = pt0 + pl;
         PM pm;
         pm.factor(D, p.eta1 + n * D, p.eta2d + n * D, prec + (size_t)k * PL);
-        nbad += pm.bad;
+        if (sp == 0) nbad += pm.bad;
         const T* tr = trec + (size_t)k * TL;
         const T cden = tr[D * D + D], nu = tr[D * D + D + 1];
         const uint64_t pair = (uint64_t)n * K + k, gpair = pair + p.pair_offset;
         T snum = T(0), sden = T(0);
-        for (int s = 0; s < S; ++s) {
+        for (int s = sp; s < S; s += split) {
             T eps[D], x[D];
             if (p.noise != nullptr) {
 #pragma unroll
@@ -271,9 +275,12 @@ __global__ void __launch_bounds__(SM_THREADS) svae_small_step_kernel(const Small
             snum += T(-0.5) * e2;
             sden += den_logprob<T>(p.den_mode, D, PM::maha(D, tr, x), cden, nu);
         }
-        sc[q] = pm.score;
-        tnum[q] = snum / T(S) + pm.hld - T(0.5 * VMP_LOG_2PI) * T(D);
-        tden[q] = sden / T(S);
+        if (sp == 0) {
+            sc[q] = pm.score;
+            snum += T(S) * (pm.hld - T(0.5 * VMP_LOG_2PI) * T(D));
+        }
+        atomicAdd(&tnum[q], snum / T(S));
+        atomicAdd(&tden[q], sden / T(S));
     }
     __syncthreads();
     // ---------------- per-point log-sum-exp, Gumbel-max selection (phase 2), log r / z / x_sample out
@@ -369,8 +376,9 @@ template <typename T> size_t small_step_smem(int K, int D, int ppc) {
 template <typename T, int D>
 static int launch_small_step(SmallStepParams<T> p, cudaStream_t st) {
     const int64_t pairs = (int64_t)p.N * p.K;
+    p.split = p.S < 4 ? p.S : 4;
     int C = 1;
-    while (C < 8 && pairs > (int64_t)C * SM_THREADS) C *= 2;               // about one pair per thread, at most 8 CTAs
+    while (C < 16 && pairs * p.split > (int64_t)C * SM_THREADS) C *= 2;    // about one work item per thread, at most 16 CTAs
     if ((int64_t)((p.N + C - 1) / C) * p.K > SM_MAX_PAIRS_PER_CTA) return -100;
     p.ppc = (p.N + C - 1) / C;
     const size_t smem = small_step_smem<T>(p.K, D, p.ppc);
@@ -378,6 +386,10 @@ static int launch_small_step(SmallStepParams<T> p, cudaStream_t st) {
     auto kern = svae_small_step_kernel<T, D>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (C > 8) {                                                            // 16 CTAs: non-portable cluster size
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return (int)e;
     }
     cudaLaunchConfig_t cfg = {};
@@ -412,7 +424,7 @@ int svae_small_step(int64_t N, int K, int D, int S, int den_mode, int only_alpha
     if (!prior[0] || !theta_out[0]) return VMP_E_BADARG;
     if (!only_alpha) for (int i = 0; i < 5; ++i) if (!prior[i] || !theta_out[i]) return VMP_E_BADARG;
     SmallStepParams<T> p;
-    p.N = (int)N; p.K = K; p.S = S; p.den_mode = den_mode; p.only_alpha = only_alpha; p.ppc = 0;
+    p.N = (int)N; p.K = K; p.S = S; p.den_mode = den_mode; p.only_alpha = only_alpha; p.ppc = 0; p.split = 1;
     p.eta1 = eta1; p.eta2d = eta2d; p.eta1_phi2 = eta1_phi2; p.L_raw = L_raw; p.pi_raw = pi_raw;
     p.th0 = theta[0]; p.th1 = theta[1]; p.th2 = theta[2]; p.th3 = theta[3]; p.th4 = nth == 5 ? theta[4] : nullptr;
     p.p0 = prior[0]; p.p1 = only_alpha ? nullptr : prior[1]; p.p2 = only_alpha ? nullptr : prior[2];

@@ -357,7 +357,7 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
     nslices = (int)((N + pps - 1) / pps);
     const size_t smem = sizeof(T) * 2 * ((size_t)SS_CH * D4 + 2 * (size_t)SS_CH * KC);
     auto kern = suffstats_kernel<T>;
-    if (smem > 48 * 1024) {
+    if (smem + 256 > 48 * 1024) {          // the kernel also has a few bytes of static shared memory (ticket of the fused tail)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
