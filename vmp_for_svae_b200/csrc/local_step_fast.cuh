@@ -63,9 +63,14 @@ template <int D, int BS_> struct FastGeom {
     static constexpr int GS = ((GS_RAW - BS + 31) / 32) * 32 + BS;
 };
 
+#ifndef VMP_D32_LANES
+#define VMP_D32_LANES 4
+#endif
+
 template <int D, int BS> struct FastLaunch;
 template <> struct FastLaunch<64, 16> { static constexpr int WARPS = 8, MINB = 1; };
 template <> struct FastLaunch<32, 8> { static constexpr int WARPS = 8, MINB = 2; };
+template <> struct FastLaunch<32, 4> { static constexpr int WARPS = 8, MINB = 1; };     // 8 rows per lane, 8 pairs per warp
 template <> struct FastLaunch<16, 4> { static constexpr int WARPS = 8, MINB = 2; };
 
 __host__ __device__ inline int fast_rec_len(int D) { return 2 * D * (D + 4) + 2 * D + 8; }

@@ -43,6 +43,7 @@ class SVAEStep(object):
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)   # ticket counter of the fused NG tail
         # launch-bound shapes on one GPU (C1 / C2): the whole step is ONE kernel on a thread-block cluster
         self.single_launch = (not self.use_dist) and core.small_step_supported(self.N, K, D)
+        self._bound = None
 
     def step(self, phi_enc, phi_gmm, theta, prior, rho, seed=0, noise=None, u=None, only_alpha=False,
              kernel_events=None):
@@ -50,10 +51,23 @@ class SVAEStep(object):
         valid on the current stream).  elbo_acc = [sum r*num, sum r*den, regulariser, #bad pivots] over ALL ranks."""
         eta1, eta2_diag = phi_enc
         if self.single_launch and kernel_events is None:
-            return core.small_step(eta1, eta2_diag, phi_gmm, theta, [prior[0]] if only_alpha else prior,
-                                   [theta[0]] if only_alpha else theta, rho, self.S, den_mode=self.den_mode,
-                                   only_alpha=only_alpha, noise=noise, u=u, seed=seed, point_offset=self.point_offset,
-                                   log_r=self.log_r, x_sample=self.x_sample, z=self.z, stats=self.stats, elbo_acc=self.elbo_acc)
+            pr, to = ([prior[0]], [theta[0]]) if only_alpha else (prior, theta)
+            b = self._bound
+            if b is not None:
+                k = b.key                     # same tensors as last time?  (theta is updated in place: a loop binds once)
+                ts = (eta1, eta2_diag) + tuple(phi_gmm) + tuple(theta) + tuple(pr) + tuple(to)
+                if len(k) != len(ts) or any(t.data_ptr() != q for t, q in zip(ts, k)) or b.only_alpha != bool(only_alpha):
+                    b = None
+            if b is None:
+                b = core.BoundSmallStep(eta1, eta2_diag, phi_gmm, theta, pr, to, self.S, self.den_mode, only_alpha, self.log_r,
+                                        self.x_sample, self.z, self.stats, self.elbo_acc, point_offset=self.point_offset)
+                b.only_alpha = bool(only_alpha)
+                self._bound = b
+            if noise is not None:
+                noise = core._chk(noise, (self.N, self.K, self.D, self.S), self.dtype, 'noise')
+            if u is not None:
+                u = core._chk(u, (self.N, self.K), self.dtype, 'u (gumbel uniforms)')
+            return b(rho, seed=seed, noise=noise, u=u)
         core.phi_prepare(phi_gmm[0], phi_gmm[1], phi_gmm[2], out=self.phi_rec)
         if self.den_mode == core.DEN_GAUSS:
             core.theta_prepare_gauss(theta, out=self.theta_rec)
