@@ -601,7 +601,9 @@ def test_sharded_inkernel_noise_equals_full_batch(shape):
         assert torch.equal(o['log_r'], of['log_r'][a:b]) and torch.equal(o['z'], of['z'][a:b])
         assert torch.equal(o['x_sample'], of['x_sample'][a:b])
         red += sh.red
-    torch.testing.assert_close(red[:-1], full.red[:-1], rtol=1e-9, atol=1e-9)
+    # same draws, hence the same per-point terms; the fp32 partial sums inside the statistics kernel cover different runs of
+    # points once the batch is cut, so the totals agree to fp32 summation accuracy at the scale of the block
+    assert float((red[:-1] - full.red[:-1]).abs().max()) <= 2e-6 * float(full.red[:-1].abs().max())
     # chunked host pipeline, in-kernel noise
     host = tuple(t.cpu().pin_memory() for t in pe)
     ch = SVAEStep(N, K, D, S, dtype=dt, device=DEV, use_dist=False)
