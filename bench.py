@@ -259,6 +259,8 @@ def fp32_peak_measured():
 
 
 def cpu_baseline_leg(args, K, D, S, rho):
+    if args.no_cpu_baseline:
+        return {'value': None, 'unit': 'points/s', 'cores': 0, 'kind': 'port', 'sample': 'skipped (--no-cpu-baseline)'}
     sample = cpu_sample_size(args, K, D)
     try:
         rate, sec, cores = cpu_rate(args, K, D, S, rho, sample, steps=2, warmup=1)
@@ -595,6 +597,7 @@ def main():
                     help='weak: the workload\'s points PER GPU; strong: the named config\'s total points divided over the ranks')
     ap.add_argument('--points', type=int, default=0, help='points per GPU (weak) / in total (strong); default: the workload\'s')
     ap.add_argument('--cpu-sample', type=int, default=0, help='points per step of the CPU reference arm')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (per-shape sweeps at several GPU counts)')
     ap.add_argument('--e2e-outputs', default='theta', choices=['theta', 'all'],
                     help='what the end-to-end leg copies back: ELBO + updated theta, or also log_r and x_sample')
     args = ap.parse_args()
