@@ -138,8 +138,9 @@ int vmp_svae_small_step_f64(int64_t N, int K, int D, int S, int den_mode, int on
  * (device scalar, may be NULL) overrides greg so that no host synchronisation is needed (CUDA-graph capture).
  * theta_rec_bar[K, vmp_theta_record_len(D)] (may be NULL) receives the gradient w.r.t. the theta record (W lower | m |
  * cden, zeros): compute_elbo_smm trains mu_k, L_k of the Student-t components by gradient (svae.py:265-322 has no
- * stop_gradient on them; experiments.py:154-174).  The in-kernel noise is keyed with point_offset 0.  D <= VMP_BWD_MAX_D, K <= 256.  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
-#define VMP_BWD_MAX_D 16
+ * stop_gradient on them; experiments.py:154-174).  The in-kernel noise is keyed with point_offset 0.  D <= 16 and K <= 256: thread-per-pair kernel; larger D (<= 64) or K: one CTA
+ * per point with the pair's matrices in shared memory (block-cooperative Cholesky / triangular inverse / Murray reverse).  workspace: vmp_svae_local_step_bwd_workspace_bytes(K, D) bytes.            */
+#define VMP_BWD_MAX_D 64
 size_t vmp_svae_local_step_bwd_workspace_bytes(int K, int D);
 int vmp_svae_local_step_bwd_f32(int64_t N, int K, int D, int S, const float* eta1, const float* eta2_diag,
                                 const float* eta1_phi2, const float* L_raw, const float* pi_raw, const float* phi_rec,

@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
 BWD_SHAPES = [(100, 10, 2, 10), (274, 10, 6, 10), (33, 5, 11, 3), (257, 32, 8, 2), (40, 3, 16, 1), (130, 1, 5, 2),
-              (1, 3, 4, 1), (61, 200, 3, 1)]
+              (1, 3, 4, 1), (61, 200, 3, 1),
+              # D > 16 / K > 256: the block-cooperative kernel (one CTA per point, matrices in shared memory)
+              (64, 12, 32, 1), (40, 9, 64, 1), (20, 5, 24, 2), (9, 4, 48, 3), (12, 300, 3, 1)]
 
 
 def _inputs(N, K, D, S, seed, student):

@@ -296,6 +296,277 @@ __global__ void __launch_bounds__(256) local_step_bwd_kernel(int64_t N, int K, i
     }
 }
 
+// ---- D > 16: one CTA per POINT, the D x D matrices of the current (point, component) pair live in shared memory and every
+// step (Cholesky, triangular inverse, the Murray reverse products) is block-cooperative.  Two passes over the components: the
+// first only evaluates glr' = glr + greg r (mean_s(num - den) + 1) for the log-soft-max reverse (needs sum_k glr'), the second
+// recomputes the factorisation and finishes as the thread-per-pair kernel above does.  Same formulas, same accumulators.
+constexpr int BWB_THREADS = 256;
+
+template <typename T>
+__device__ void bwb_chol(T* A, int D, int ld) {                      // in place, lower; all threads
+    for (int j = 0; j < D; ++j) {
+        __syncthreads();
+        const T djj = t_sqrt(A[j * ld + j]);
+        __syncthreads();
+        if (threadIdx.x == 0) A[j * ld + j] = djj;
+        const T inv = T(1) / djj;
+        for (int i = j + 1 + threadIdx.x; i < D; i += blockDim.x) A[i * ld + j] *= inv;
+        __syncthreads();
+        const int m = D - j - 1;
+        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+            const int i = j + 1 + e / m, c = j + 1 + e % m;
+            if (c <= i) A[i * ld + c] = fma(-A[i * ld + j], A[c * ld + j], A[i * ld + c]);
+        }
+    }
+    __syncthreads();
+}
+
+template <typename T, bool TH>
+__global__ void __launch_bounds__(BWB_THREADS)
+local_step_bwd_block_kernel(int64_t N, int K, int D, int S, int den_mode, const T* __restrict__ eta1,
+                            const T* __restrict__ eta2d, const T* __restrict__ phi_rec, const T* __restrict__ theta_rec,
+                            const T* __restrict__ noise, uint64_t seed, const T* __restrict__ log_r, const T* __restrict__ gx,
+                            const T* __restrict__ glr, T greg_host, const T* __restrict__ greg_dev, T* __restrict__ eta1_bar,
+                            T* __restrict__ eta2d_bar, double* __restrict__ kacc) {
+    const T greg = greg_dev != nullptr ? *greg_dev : greg_host;
+    const int ld = D + 1, tid = threadIdx.x, nth = blockDim.x;
+    const int64_t n = blockIdx.x;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double* pacc = reinterpret_cast<double*>(smraw);                 // [2D]
+    T* Lc = reinterpret_cast<T*>(pacc + 2 * D);                      // chol(P~)
+    T* Li = Lc + D * ld;                                             // L^-1
+    T* Sg = Li + D * ld;                                             // P~^-1
+    T* Lb = Sg + D * ld;                                             // L_bar -> X
+    T* B5 = Lb + D * ld;                                             // Phi -> Sm -> Pt_bar
+    T* Wb = B5 + D * ld;                                             // d/dW (TH only; else zero-sized use)
+    T* vecs = Wb + (TH ? D * ld : 0);
+    T *p1 = vecs, *mu1 = p1 + D, *dv = mu1 + D, *gq = dv + D, *mut = gq + D, *bv = mut + D, *gmu = bv + D, *eps = gmu + D,
+      *u = eps + D, *xm = u + D, *wx = xm + D, *Gx = wx + D, *tv = Gx + D, *v = tv + D, *dbar = v + D, *mb = dbar + D,
+      *hh = mb + D, *glrp = hh + D;                                  // glrp[K]
+    __shared__ double red[32];
+    __shared__ T sh_scalar[4];
+    const int plen = phi_record_len(D), tlen = theta_record_len(D), kl = bwd_klen(D);
+    for (int i = tid; i < D; i += nth) {
+        p1[i] = T(-2) * eta2d[n * D + i];
+        mu1[i] = eta1[n * D + i] / p1[i];
+    }
+    for (int i = tid; i < 2 * D; i += nth) pacc[i] = 0.0;
+    __syncthreads();
+    T gsum = T(0);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int k = 0; k < K; ++k) {
+            const T* prec = phi_rec + (size_t)k * plen;
+            const T* P2 = prec;
+            const T* trec = theta_rec + (size_t)k * tlen;
+            const T* W = trec;
+            const T* mth = trec + D * D;
+            __syncthreads();
+            for (int e = tid; e < D * D; e += nth) {
+                const int i = e / D, j = e - i * D;
+                Lc[i * ld + j] = P2[e] + (i == j ? p1[i] : T(0));
+            }
+            for (int i = tid; i < D; i += nth) {
+                dv[i] = mu1[i] - prec[D * D + i];
+                hh[i] = eta1[n * D + i] + prec[D * D + D + i];
+                gmu[i] = T(0);
+                if (TH) mb[i] = T(0);
+            }
+            bwb_chol(Lc, D, ld);
+            for (int j = tid; j < D; j += nth) {                      // Li = L^-1, thread per column
+                for (int i = 0; i < j; ++i) Li[i * ld + j] = T(0);
+                Li[j * ld + j] = T(1) / Lc[j * ld + j];
+                for (int i = j + 1; i < D; ++i) {
+                    T sacc = T(0);
+                    for (int c = j; c < i; ++c) sacc = fma(Lc[i * ld + c], Li[c * ld + j], sacc);
+                    Li[i * ld + j] = -sacc / Lc[i * ld + i];
+                }
+            }
+            double hl = 0.0;
+            for (int i = tid; i < D; i += nth) hl += (double)t_log(Lc[i * ld + i]);
+            hl = block_sum(hl, red);
+            if (tid == 0) sh_scalar[0] = (T)hl;
+            __syncthreads();
+            const T hldv = sh_scalar[0];
+            // Sig = L^-T L^-1 (pass 1 needs the matrix; pass 0 only mu~ = Sig (eta1 + h2), done with it as well)
+            for (int e = tid; e < D * D; e += nth) {
+                const int i = e / D, j = e - i * D;
+                if (j > i) continue;
+                T sacc = T(0);
+                for (int c = i; c < D; ++c) sacc = fma(Li[c * ld + i], Li[c * ld + j], sacc);
+                Sg[i * ld + j] = sacc;
+                Sg[j * ld + i] = sacc;
+            }
+            for (int i = tid; i < D; i += nth) {
+                T sacc = T(0);
+                for (int c = 0; c < D; ++c) sacc = fma(P2[i * D + c], dv[c], sacc);
+                gq[i] = sacc;
+            }
+            __syncthreads();
+            for (int i = tid; i < D; i += nth) {
+                T s0 = T(0), s1 = T(0);
+                for (int c = 0; c < D; ++c) {
+                    s0 = fma(Sg[i * ld + c], hh[c], s0);
+                    s1 = fma(Sg[i * ld + c], gq[c], s1);
+                }
+                mut[i] = s0;
+                bv[i] = s1;
+            }
+            if (pass == 1) {
+                for (int e = tid; e < D * ld; e += nth) { Lb[e] = T(0); if (TH) Wb[e] = T(0); }
+            }
+            __syncthreads();
+            const T r = t_exp(log_r[n * K + k]);
+            const T nu = trec[D * D + D + 1];
+            const uint64_t pair = (uint64_t)n * K + k;
+            T Tsum = T(0);
+            for (int s = 0; s < S; ++s) {
+                for (int i = tid; i < D; i += nth)
+                    eps[i] = noise != nullptr ? noise[(pair * D + i) * (uint64_t)S + s]
+                                              : (T)philox_normal1(seed, pair, (uint32_t)s, (uint32_t)i);
+                __syncthreads();
+                for (int i = tid; i < D; i += nth) {                  // u = L^-T eps = Li^T eps ; xm = mu~ + u - m_theta
+                    T sacc = T(0);
+                    for (int c = i; c < D; ++c) sacc = fma(Li[c * ld + i], eps[c], sacc);
+                    u[i] = sacc;
+                    xm[i] = mut[i] + sacc - mth[i];
+                }
+                __syncthreads();
+                double q2d = 0.0, e2d = 0.0;
+                for (int i = tid; i < D; i += nth) {                  // wx = W (x - m)
+                    T sacc = T(0);
+                    for (int c = 0; c <= i; ++c) sacc = fma(W[i * D + c], xm[c], sacc);
+                    wx[i] = sacc;
+                    q2d += (double)sacc * (double)sacc;
+                    e2d += (double)eps[i] * (double)eps[i];
+                }
+                q2d = block_sum(q2d, red);
+                e2d = block_sum(e2d, red);
+                if (tid == 0) { sh_scalar[1] = (T)q2d; sh_scalar[2] = (T)e2d; }
+                __syncthreads();
+                const T q2 = sh_scalar[1], e2 = sh_scalar[2];
+                const T num = T(-0.5) * e2 + hldv - T(0.5 * VMP_LOG_2PI) * T(D) + log_r[n * K + k];
+                const T den = den_mode == VMP_DEN_GAUSS ? trec[D * D + D] - T(0.5) * q2
+                                                        : trec[D * D + D] - T(0.5) * (nu + T(D)) * t_log1p(q2 / nu);
+                Tsum += num - den;
+                if (pass == 1) {
+                    const T coef = den_mode == VMP_DEN_GAUSS ? T(1) : (nu + T(D)) / (nu + q2);
+                    const T cf = greg / T(S) * r * coef;
+                    const T* gxs = gx + ((pair * S) + s) * (uint64_t)D;
+                    for (int i = tid; i < D; i += nth) {              // Gx = gx + greg/S r coef W^T wx
+                        T sacc = T(0);
+                        for (int c = i; c < D; ++c) sacc = fma(W[c * D + i], wx[c], sacc);
+                        const T gden = cf * sacc;
+                        Gx[i] = gxs[i] + gden;
+                        gmu[i] += Gx[i];
+                        if (TH) mb[i] -= gden;
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < D; i += nth) {              // t = L^-1 Gx
+                        T sacc = T(0);
+                        for (int c = 0; c <= i; ++c) sacc = fma(Li[i * ld + c], Gx[c], sacc);
+                        tv[i] = sacc;
+                    }
+                    __syncthreads();
+                    for (int e = tid; e < D * D; e += nth) {
+                        const int i = e / D, j = e - i * D;
+                        if (j > i) continue;
+                        Lb[i * ld + j] = fma(-u[i], tv[j], Lb[i * ld + j]);
+                        if (TH) Wb[i * ld + j] = fma(cf * wx[i], xm[j], Wb[i * ld + j]);
+                    }
+                }
+                __syncthreads();
+            }
+            if (pass == 0) {
+                if (tid == 0) glrp[k] = glr[n * K + k] + greg * r * (Tsum / T(S) + T(1));
+                continue;
+            }
+            // ---------------- finish (pass 1)
+            const T s_bar = glrp[k] - r * gsum;
+            const T hld_bar = greg * r - s_bar;
+            for (int i = tid; i < D; i += nth) {                      // v = Sig gmu
+                T sacc = T(0);
+                for (int c = 0; c < D; ++c) sacc = fma(Sg[i * ld + c], gmu[c], sacc);
+                v[i] = sacc;
+            }
+            for (int e = tid; e < D * D; e += nth) {                  // Phi = tril(L^T L_bar), diagonal halved -> B5
+                const int i = e / D, j = e - i * D;
+                if (j > i) { B5[i * ld + j] = T(0); continue; }
+                T sacc = T(0);
+                for (int c = i; c < D; ++c) sacc = fma(Lc[c * ld + i], Lb[c * ld + j], sacc);
+                B5[i * ld + j] = (i == j) ? T(0.5) * sacc : sacc;
+            }
+            __syncthreads();
+            for (int e = tid; e < D * D; e += nth) {                  // X = Phi L^-1 (lower) -> Lb
+                const int i = e / D, j = e - i * D;
+                T sacc = T(0);
+                if (j <= i)
+                    for (int c = j; c <= i; ++c) sacc = fma(B5[i * ld + c], Li[c * ld + j], sacc);
+                Lb[i * ld + j] = sacc;
+            }
+            __syncthreads();
+            for (int e = tid; e < D * D; e += nth) {                  // Sm = L^-T X -> B5
+                const int i = e / D, j = e - i * D;
+                T sacc = T(0);
+                for (int c = (i > j ? i : j); c < D; ++c) sacc = fma(Li[c * ld + i], Lb[c * ld + j], sacc);
+                B5[i * ld + j] = sacc;
+            }
+            __syncthreads();
+            for (int e = tid; e < D * D; e += nth) {                  // Pt_bar (symmetric) in place
+                const int i = e / D, j = e - i * D;
+                if (j > i) continue;
+                const T sm = T(0.5) * (B5[i * ld + j] + B5[j * ld + i]);
+                const T val = sm - T(0.5) * (v[i] * mut[j] + mut[i] * v[j]) + T(0.5) * hld_bar * Sg[i * ld + j] -
+                              T(0.5) * s_bar * bv[i] * bv[j];
+                B5[i * ld + j] = val;
+                B5[j * ld + i] = val;
+            }
+            for (int i = tid; i < D; i += nth) {                      // d_bar = -s_bar P2 (d - b)
+                T sacc = T(0);
+                for (int c = 0; c < D; ++c) sacc = fma(P2[i * D + c], dv[c] - bv[c], sacc);
+                dbar[i] = -s_bar * sacc;
+            }
+            __syncthreads();
+            double* ka = kacc + (size_t)k * kl;
+            for (int i = tid; i < D; i += nth) {
+                pacc[i] += (double)(v[i] + dbar[i] / p1[i]);
+                pacc[D + i] += (double)(B5[i * ld + i] - dbar[i] * mu1[i] / p1[i]);
+                atomicAdd(ka + D * D + i, (double)v[i]);
+                atomicAdd(ka + D * D + D + i, (double)(-dbar[i]));
+                if (TH) atomicAdd(ka + D * D + 2 * D + 1 + D * D + i, (double)mb[i]);
+            }
+            for (int e = tid; e < D * D; e += nth) {
+                const int i = e / D, j = e - i * D;
+                const T val = B5[i * ld + j] - T(0.5) * s_bar * (dv[i] * dv[j] - dv[i] * bv[j] - bv[i] * dv[j]);
+                atomicAdd(ka + e, (double)val);
+                if (TH && j <= i) atomicAdd(ka + D * D + 2 * D + 1 + e, (double)Wb[i * ld + j]);
+            }
+            if (tid == 0) {
+                atomicAdd(ka + D * D + 2 * D, (double)s_bar);
+                if (TH) atomicAdd(ka + D * D + 2 * D + 1 + D * D + D, (double)(-greg * r));
+            }
+        }
+        if (pass == 0) {
+            __syncthreads();
+            double gs = 0.0;
+            for (int k = tid; k < K; k += nth) gs += (double)glrp[k];
+            gs = block_sum(gs, red);
+            if (tid == 0) sh_scalar[3] = (T)gs;
+            __syncthreads();
+            gsum = sh_scalar[3];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < D; i += nth) {
+        eta1_bar[n * D + i] = (T)pacc[i];
+        eta2d_bar[n * D + i] = (T)(-2.0 * pacc[D + i]);
+    }
+}
+
+template <typename T>
+static size_t bwb_smem(int K, int D, bool th) {
+    return sizeof(double) * 2 * D + sizeof(T) * ((size_t)(th ? 6 : 5) * D * (D + 1) + 17 * (size_t)D + K) + 32;
+}
+
 // K-sized epilogue: (P2_bar, h2_bar, mu2_bar, s_sum) -> (eta1_phi2_bar, L_raw_bar, pi_raw_bar)
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -414,8 +685,10 @@ static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, co
                                const T* noise, uint64_t seed, const T* log_r, const T* gx, const T* glr, double greg,
                                const T* greg_dev, T* eta1_bar, T* eta2d_bar, T* h2_bar, T* L_raw_bar, T* pi_raw_bar,
                                T* theta_rec_bar, void* work, size_t work_bytes, cudaStream_t st) {
-    if (N < 0 || K < 1 || K > 256 || S < 1) return VMP_E_BADARG;
-    if (D < 1 || D > BWD_MAX_D) return VMP_E_BADDIM;
+    if (N < 0 || K < 1 || S < 1) return VMP_E_BADARG;
+    if (D < 1 || D > VMP_MAX_D) return VMP_E_BADDIM;
+    const bool block_path = D > BWD_MAX_D || K > 256;            // matrices in shared memory, one CTA per point
+    if (block_path && bwb_smem<T>(K, D, theta_rec_bar != nullptr) > 220 * 1024) return VMP_E_BADARG;
     if (den_mode != VMP_DEN_GAUSS && den_mode != VMP_DEN_STUDENT) return VMP_E_BADMODE;
     const size_t kl = (size_t)bwd_klen(D);
     if (!work || work_bytes < (size_t)K * kl * sizeof(double)) return VMP_E_BADARG;
@@ -426,6 +699,24 @@ static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, co
         if (!eta1 || !eta2d || !phi_rec || !theta_rec || !log_r || !gx || !glr || !eta1_bar || !eta2d_bar)
             return VMP_E_BADARG;
         cudaError_t e;
+        if (block_path) {
+            const size_t sm = bwb_smem<T>(K, D, theta_rec_bar != nullptr);
+            if (N > 0x7fffffffLL) return VMP_E_BADARG;
+            if (theta_rec_bar) {
+                auto kern = local_step_bwd_block_kernel<T, true>;
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                if (e != cudaSuccess) return (int)e;
+                kern<<<(unsigned)N, BWB_THREADS, sm, st>>>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise, seed, log_r,
+                                                          gx, glr, (T)greg, greg_dev, eta1_bar, eta2d_bar, kacc);
+            } else {
+                auto kern = local_step_bwd_block_kernel<T, false>;
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+                if (e != cudaSuccess) return (int)e;
+                kern<<<(unsigned)N, BWB_THREADS, sm, st>>>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise, seed, log_r,
+                                                          gx, glr, (T)greg, greg_dev, eta1_bar, eta2d_bar, kacc);
+            }
+            e = cudaGetLastError();
+        } else {
 #define VMP_BWD_CASE(DD)                                                                                              \
     case DD:                                                                                                          \
         e = theta_rec_bar ? launch_bwd_main<T, DD, true>(N, K, D, S, den_mode, eta1, eta2d, phi_rec, theta_rec, noise,   \
@@ -444,6 +735,7 @@ static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, co
                                                                  kacc, st);
         }
 #undef VMP_BWD_CASE
+        }
         if (e != cudaSuccess) return (int)e;
     }
     const size_t esm = (size_t)(4 * D * (D + 1) + 3 * D + 32) * sizeof(double);
