@@ -134,3 +134,33 @@ def test_graphed_trainer_trains_and_is_faster(method):
     assert abs(float(tr.rho) - 0.1 * 0.95 ** (tr.global_step / 1000.0)) < 1e-9
     print('graphed training iteration: %.3f ms' % ms)
     assert ms < 2.0, ms            # eager iteration: 2.2-2.6 ms; measured replay: 0.52 ms (GMM), 0.65 ms (SMM)
+
+
+@pytest.mark.parametrize('method,L,U', [('svae-cvi', 3, 20), ('svae-cvi-smm', 2, 16), ('svae-cvi', 32, 24)],
+                         ids=['gmm-L3', 'smm-L2', 'gmm-L32'])
+def test_streamed_iteration_equals_whole_batch(method, L, U):
+    """SVAETrainer.train_step_streamed (x_k_samples produced, decoded and back-propagated tile by tile: the [N,K,S,D] tensor of
+    svae.py:511 never exists for the whole batch) == train_step on the whole batch: same ELBO, same parameter gradients, same
+    CVI update.  L = 32 also exercises the block-cooperative reverse kernel inside a training iteration (C4-shaped latent)."""
+    import copy
+    import numpy as np
+    from vmp_for_svae_b200 import experiments as ex
+    cfg = dict(dataset='pinwheel', method=method, lr=0.01, lrcvi=0.1, K=7, L=L, U=U, DoF=5, seed=2)
+    a = ex.SVAETrainer(cfg, obs_dim=5, device='cuda:0', nb_samples=2, stddev_init_nn=0.2)
+    b = copy.deepcopy(a)
+    y = torch.as_tensor(np.random.RandomState(1).randn(83, 5) * 1.5, dtype=torch.float32, device='cuda:0')
+    grads = []
+    for tr, step in ((a, lambda t: t.train_step(y)), (b, lambda t: t.train_step_streamed(y, 17))):
+        caught = {}
+        orig = tr.opt.step
+        tr.opt.step = lambda tr=tr, caught=caught, orig=orig: caught.update(
+            g=[p.grad.detach().clone() for grp in tr.opt.param_groups for p in grp['params']]) or orig()
+        out = step(tr)
+        grads.append((out, caught['g'], [t.clone() for t in (tr.theta if not tr.smm else [tr.alpha])]))
+    (oa, ga, ta), (ob_, gb, tb) = grads
+    assert float(oa['bad_pivots']) == 0 and float(ob_['bad_pivots']) == 0
+    assert abs(float(oa['elbo']) - float(ob_['elbo'])) <= 2e-5 * abs(float(oa['elbo']))
+    for x, z in zip(ga, gb):
+        assert float((x - z).abs().max()) <= 2e-4 * max(float(x.abs().max()), 1e-6)
+    for x, z in zip(ta, tb):
+        torch.testing.assert_close(z, x, rtol=2e-5, atol=1e-5)

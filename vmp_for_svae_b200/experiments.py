@@ -223,6 +223,44 @@ class SVAETrainer(object):
         self.global_step += 1
         return dict(elbo=elbo.detach(), neg_rec=neg_rec.detach(), reg=reg.detach(), bad_pivots=acc[3])
 
+    def train_step_streamed(self, y, tile_points):
+        """The same iteration as `train_step`, with x_k_samples STREAMED to the decoder tile by tile (SURVEY 8f row 2;
+        svae.py:511 `decoder(x_k_samples)` on the whole [N,K,S,D] tensor, vae.py:138-151): the points are cut into tiles of
+        `tile_points`; per tile: encoder -> fused local step (its samples [tile,K,S,D] only) -> decoder -> weighted
+        log-likelihood -> backward, which frees the tile's samples and decoder activations before the next tile is produced.
+        The ELBO is a sum over points given (phi_gmm, theta), so parameter gradients simply accumulate over the tiles and the
+        statistics of the CVI step accumulate in one buffer.  The noise is the batch-level Philox stream (keyed by the global
+        point index), i.e. exactly the draws of the untiled call."""
+        seed = (self.cfg.get('seed', 0) << 32) + self.global_step
+        N, K, L, S = y.shape[0], self.K, self.L, self.S
+        den = core.DEN_STUDENT if self.smm else core.DEN_GAUSS
+        self.opt.zero_grad(set_to_none=True)
+        stats, tot, bad = None, torch.zeros(3, device=self.dev), 0
+        for lo in range(0, N, int(tile_points)):
+            hi = min(N, lo + int(tile_points))
+            yt = y[lo:hi]
+            noise, u = core.fill_noise(hi - lo, K, L, S, seed, torch.float32, self.dev, point_offset=lo)
+            eta1, eta2d = self.encoder(yt)
+            x_k, log_r, reg, acc, x_samp, z = local_step_autograd(
+                eta1, eta2d, self.phi_gmm[0], self.phi_gmm[1], self.phi_gmm[2], self.theta_record(), S, den_mode=den,
+                noise=noise, u=u, full=True)
+            neg_rec = decoder_loglike_autograd(yt, self.decoder(x_k), torch.exp(log_r), self.decoder_type)
+            (-(neg_rec - reg)).backward()
+            with torch.no_grad():
+                tot += torch.stack([neg_rec.detach() - reg.detach(), neg_rec.detach(), reg.detach()])
+                xs = torch.zeros(hi - lo, 1, device=self.dev) if self.smm else x_samp
+                stats = core.suffstats(xs, log_r.detach(), r_is_log=True, stats=stats)
+                bad = bad + acc[3]
+            del x_k, log_r, reg, neg_rec, noise
+        rho = self.lrcvi()
+        if self.smm:
+            core.ng_update(stats, rho, self.prior, [self.alpha], only_alpha=True)
+        else:
+            core.ng_update(stats, rho, self.prior, self.theta)
+        self.opt.step()
+        self.global_step += 1
+        return dict(elbo=tot[0], neg_rec=tot[1], reg=tot[2], bad_pivots=bad)
+
     @torch.no_grad()
     def evaluate(self, y, labels=None, nb_samples=100, seed=12345):
         """experiments.py:262-304 : test-time inference with S=100 -> mse, log-likelihood, (entropy, purity);
