@@ -739,6 +739,10 @@ static int svae_local_step_bwd(int64_t N, int K, int D, int S, const T* eta1, co
         if (e != cudaSuccess) return (int)e;
     }
     const size_t esm = (size_t)(4 * D * (D + 1) + 3 * D + 32) * sizeof(double);
+    if (esm + 256 > 48 * 1024) {
+        cudaError_t ee = cudaFuncSetAttribute(local_step_bwd_epilogue_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm);
+        if (ee != cudaSuccess) return (int)ee;
+    }
     local_step_bwd_epilogue_kernel<T><<<K, 128, esm, st>>>(K, D, eta1_phi2, L_raw, pi_raw, kacc, h2_bar, L_raw_bar,
                                                            pi_raw_bar, theta_rec_bar);
     return launch_status();
