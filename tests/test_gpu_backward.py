@@ -118,7 +118,7 @@ def test_backward_through_selected_sample_and_decoder():
 
 def test_backward_argument_errors():
     from vmp_for_svae_b200 import core
-    N, K, D, S = 4, 2, 17, 1
+    N, K, D, S = 4, 2, 65, 1            # latent dimensions up to 64 are supported (block-cooperative kernel above 16)
     z = lambda *s: torch.zeros(*s, dtype=torch.float64, device=DEV)
     plen, tlen, _ = __import__('vmp_for_svae_b200')._lib.record_lens(D)
     with pytest.raises(ValueError):
