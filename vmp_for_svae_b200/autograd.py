@@ -10,7 +10,7 @@ tf.stop_gradient (svae.py:211-214).  Here those three are ONE forward kernel and
     x_k, log_r, reg = local_step_autograd(eta1, eta2_diag, eta1_phi2, L_raw, pi_raw, theta_rec, S, seed=...)
     loss = -(decoder_loglike(x_k gathered at z) - reg);  loss.backward()
 
-Latent dimension <= 16 and K <= 256 in the backward (the reference's training shapes are D = 2, 6; K = 10).
+Latent dimension <= 64 in the backward (thread-per-pair kernel up to D = 16, block-cooperative kernel above).
 """
 import torch
 
