@@ -236,7 +236,8 @@ def replicas_identical(tensors, world, dev):
     for t in tensors:
         ref = t.clone()
         torch.distributed.broadcast(ref, src=0)
-        same &= int(torch.equal(ref, t))
+        bits = torch.int64 if t.element_size() == 8 else torch.int32        # bit patterns: NaNs must compare equal too
+        same &= int(torch.equal(ref.view(bits), t.view(bits)))
     flag = torch.tensor([same], dtype=torch.int32, device=dev)
     torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
     return bool(flag.item())
@@ -505,6 +506,7 @@ def run_cuda_sweep(args):
     clocks = sampler.stop() if sampler else None
     ms_step = vdist.max_over_ranks(t0.elapsed_time(t1) / reps, dev)
     identical = replicas_identical([out['alpha_k'], out['m_k'], out['C_k']], world, dev)
+    state_finite = bool(torch.isfinite(out['C_k']).all() and torch.isfinite(r).all() and torch.isfinite(u).all())
     launches, kernels = count_kernel_launches(lambda: sw.sweep(x, r, u))
     # multi-sweep driver loop in one call (r, u stay on chip between sweeps)
     nfit = 8
@@ -579,6 +581,7 @@ def run_cuda_sweep(args):
         'fit': {'ms_per_sweep': ms_fit, 'sweeps_per_call': nfit, 'value': total_points / (ms_fit * 1e-3), 'unit': 'points/s',
                 'note': 'smm.fit: the reference\'s driver loop in one call; r, u are not written between sweeps'},
         'cpu_baseline': cpu_baseline_leg(args, K, D, 1, 0.0),
+        'state_finite_after_timed_sweeps': state_finite,
     }
     if identical is not None:
         line['replicas_bit_identical'] = identical
