@@ -1,0 +1,274 @@
+// chol64_tc.cu — stand-alone microkernel: batched Cholesky of 64 x 64 SPD systems A_b = P2[b % K] + diag(p_b) with the trailing
+// updates on the 5th-generation tensor cores ("Next round" item 2).  Blocked right-looking factorisation, NB = 16:
+//   * the trailing matrix is a TMEM accumulator: one CTA (4 warps) owns TWO systems, interleaved in one 128-lane block
+//     (M = 64 layout: row i of system A -> lane 32 (i/16) + i%16, system B at lane offset 16; probe-validated);
+//   * panel j: every thread owns ONE row (the only ownership TMEM allows): v[0..15] = P2 panel + accumulator (tcgen05.ld);
+//     the warp that holds the diagonal block factors it with half-warp shuffles and publishes L11 to shared memory; the rows
+//     below solve their 16 entries against L11 (broadcast reads), split them into tf32 hi + lo and store them K-major in the
+//     operand tile;
+//   * trailing update: D -= Lp Lp^T as 2 K-steps x 3 split terms (hi.hi + lo.hi + hi.lo) tcgen05.mma kind::tf32, M = 64, N = 64,
+//     negate-A, A and B descriptors on the SAME tile; commit -> mbarrier -> next panel.
+// Outputs L (optional) and log det; main() checks them against an fp64 Cholesky and times the kernel.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/probes/chol64_tc tools/probes/chol64_tc.cu
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+constexpr int D = 64, NB = 16;
+constexpr uint32_t LBO = 128, SBO = (NB / 4) * 128;           // K-major, no swizzle: 8 x 16-byte core matrices, K = 16 per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((LBO >> 4) & 0x3FFF) << 16) | ((uint64_t)((SBO >> 4) & 0x3FFF) << 32) |
+           ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ int tile_off(int m, int k) { return ((m / 8) * SBO + (k / 4) * LBO + (m % 8) * 16 + (k % 4) * 4) / 4; }
+__device__ __forceinline__ void mma_tf32(uint32_t taddr, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(taddr), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ float tf32_hi(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(128, 8)
+chol64_tc_kernel(int64_t B, int K, const float* __restrict__ P2, const float* __restrict__ p, float* __restrict__ Lout,
+                 float* __restrict__ logdet, int* __restrict__ status) {
+    __shared__ __align__(1024) float tile[2][2][D * NB];        // [system][hi|lo][64 x 16 K-major]
+    __shared__ float L11[2][NB][NB + 1];
+    __shared__ float invd[2][NB];
+    __shared__ float ldpart[2][4];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, sys = lane >> 4, rl = lane & 15, row = 16 * w + rl;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int e = tid; e < 2 * 2 * D * NB; e += 128) (&tile[0][0][0])[e] = 0.f;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base, tlane = taddr + ((uint32_t)(32 * w) << 16);
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 13) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+    uint32_t parity = 0;
+    bool ok = true;
+
+    for (int64_t it = blockIdx.x; 2 * it < B; it += gridDim.x) {
+        const int64_t b = 2 * it + sys;
+        const bool live = b < B;
+        const int64_t bb = live ? b : B - 1;
+        const float* Pk = P2 + (size_t)(bb % K) * D * D + (size_t)row * D;
+        const float prow = p[bb * D + row];
+        float ld_acc = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < D / NB; ++j) {
+            float v[NB];
+            if (w >= j) {                                            // rows of and below the diagonal block
+#pragma unroll
+                for (int q = 0; q < NB / 4; ++q) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(Pk + NB * j + 4 * q);
+                    v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                }
+                if (j > 0) {
+                    uint32_t a[NB];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                                   "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+                                 : "r"(tlane + (uint32_t)(NB * j)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) v[c] += __uint_as_float(a[c]);
+                }
+            }
+            if (w == j) {
+                // ---- diagonal block: right-looking Cholesky across the 16 lanes of each system (row-owned, shuffles)
+#pragma unroll
+                for (int c = 0; c < NB; ++c)
+                    if (rl == c) v[c] += prow;
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    const float piv = __shfl_sync(0xffffffffu, v[c], c, 16);
+                    const float rs = rsqrtf(piv);
+                    const float inv = rs * fmaf(-0.5f * piv * rs, rs, 1.5f);
+                    const float lc = v[c] * inv;                     // L[rl][c] (rows below c; row c itself: L_cc)
+                    v[c] = lc;
+                    if (rl == c) { ld_acc += logf(lc); invd[sys][c] = inv; }
+#pragma unroll
+                    for (int c2 = c + 1; c2 < NB; ++c2) {
+                        const float lc2 = __shfl_sync(0xffffffffu, lc, c2, 16);      // L[c2][c]
+                        v[c2] = fmaf(-lc, lc2, v[c2]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c) L11[sys][rl][c] = c <= rl ? v[c] : 0.f;
+            }
+            __syncthreads();
+            if (w > j) {
+                // ---- rows below: l[c] = (v[c] - sum_{m<c} l[m] L11[c][m]) / L11[c][c]
+#pragma unroll
+                for (int c = 0; c < NB; ++c) {
+                    float s = v[c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) s = fmaf(-v[m], L11[sys][c][m], s);
+                    v[c] = s * invd[sys][c];
+                }
+                if (j < D / NB - 1) {
+#pragma unroll
+                    for (int q = 0; q < NB / 4; ++q) {
+                        float h[4], l[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) { h[i] = tf32_hi(v[4 * q + i]); l[i] = v[4 * q + i] - h[i]; }
+                        *reinterpret_cast<float4*>(&tile[sys][0][tile_off(row, 4 * q)]) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4*>(&tile[sys][1][tile_off(row, 4 * q)]) = make_float4(l[0], l[1], l[2], l[3]);
+                    }
+                }
+            }
+            if (w >= j && Lout != nullptr && live) {
+#pragma unroll
+                for (int q = 0; q < NB / 4; ++q)
+                    *reinterpret_cast<float4*>(Lout + (size_t)b * D * D + (size_t)row * D + NB * j + 4 * q) =
+                        make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (j < D / NB - 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncthreads();
+                if (tid == 0) {
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        const uint32_t ta = taddr + ((uint32_t)(16 * s2) << 16);
+#pragma unroll
+                        for (int ks = 0; ks < NB / 8; ++ks) {
+                            const uint64_t dh = make_desc(smem_u32(&tile[s2][0][0]) + ks * 2 * LBO);
+                            const uint64_t dl = make_desc(smem_u32(&tile[s2][1][0]) + ks * 2 * LBO);
+                            mma_tf32(ta, dh, dh, IDESC, (j > 0 || ks > 0) ? 1u : 0u);
+                            mma_tf32(ta, dl, dh, IDESC, 1u);
+                            mma_tf32(ta, dh, dl, IDESC, 1u);
+                        }
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+                }
+                ok = wait_bar(&bar, parity) && ok;
+                parity ^= 1;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+        }
+        // ---- log det = 2 sum_i log L_ii
+        float s = ld_acc;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 16);
+        if (rl == 0) ldpart[sys][w] = s;
+        __syncthreads();
+        if (tid < 2 && 2 * it + tid < B) logdet[2 * it + tid] = 2.f * (ldpart[tid][0] + ldpart[tid][1] + ldpart[tid][2] + ldpart[tid][3]);
+        __syncthreads();
+    }
+    if (!ok && tid == 0) atomicExch(status, -1);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(taddr) : "memory");
+}
+
+static void chol64_host(const double* A, double* L) {
+    for (int i = 0; i < D; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = A[i * D + j];
+            for (int c = 0; c < j; ++c) s -= L[i * D + c] * L[j * D + c];
+            L[i * D + j] = i == j ? sqrt(s) : s / L[j * D + j];
+        }
+}
+
+int main(int argc, char** argv) {
+    const int K = 128;
+    const int64_t Bcheck = 512, Btime = argc > 1 ? atoll(argv[1]) : (1 << 21);
+    std::vector<float> P2((size_t)K * D * D), p((size_t)Btime * D);
+    srand(11);
+    auto rnd = []() { return (float)rand() / RAND_MAX * 2.f - 1.f; };
+    for (int k = 0; k < K; ++k) {                                   // P2_k = G G^T / D + I (SPD, off-diagonals O(0.1))
+        std::vector<float> G(D * D);
+        for (auto& g : G) g = rnd();
+        for (int i = 0; i < D; ++i)
+            for (int j = 0; j < D; ++j) {
+                double s = i == j ? 1.0 : 0.0;
+                for (int c = 0; c < D; ++c) s += (double)G[i * D + c] * G[j * D + c] / D;
+                P2[(size_t)k * D * D + i * D + j] = (float)s;
+            }
+    }
+    for (auto& v : p) v = 0.2f + 1.5f * (float)rand() / RAND_MAX;
+    float *dP2, *dp, *dL, *dld;
+    int* dst;
+    cudaMalloc(&dP2, P2.size() * 4); cudaMalloc(&dp, p.size() * 4); cudaMalloc(&dL, (size_t)Bcheck * D * D * 4);
+    cudaMalloc(&dld, (size_t)Btime * 4); cudaMalloc(&dst, 4);
+    cudaMemcpy(dP2, P2.data(), P2.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dp, p.data(), p.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(dst, 0, 4);
+    cudaMemset(dL, 0, (size_t)Bcheck * D * D * 4);
+    int occ = 0, sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol64_tc_kernel, 128, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    printf("chol64_tc: occupancy %d CTAs/SM (x2 systems each), %d SMs\n", occ, sms);
+    // ---- correctness
+    chol64_tc_kernel<<<64, 128>>>(Bcheck, K, dP2, dp, dL, dld, dst);
+    cudaError_t e = cudaDeviceSynchronize();
+    int st = 0;
+    cudaMemcpy(&st, dst, 4, cudaMemcpyDeviceToHost);
+    printf("check run: cuda=%s status=%d\n", cudaGetErrorString(e), st);
+    if (e != cudaSuccess || st != 0) return 1;
+    std::vector<float> L((size_t)Bcheck * D * D), ld(Bcheck);
+    cudaMemcpy(L.data(), dL, L.size() * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ld.data(), dld, Bcheck * 4, cudaMemcpyDeviceToHost);
+    double worstL = 0, worstld = 0;
+    for (int64_t b = 0; b < Bcheck; ++b) {
+        std::vector<double> A(D * D), Lr(D * D, 0.0);
+        for (int i = 0; i < D * D; ++i) A[i] = P2[(size_t)(b % K) * D * D + i];
+        for (int i = 0; i < D; ++i) A[i * D + i] += p[b * D + i];
+        chol64_host(A.data(), Lr.data());
+        double l2 = 0;
+        for (int i = 0; i < D; ++i) {
+            l2 += 2 * log(Lr[i * D + i]);
+            for (int j = 0; j <= i; ++j) worstL = fmax(worstL, fabs(L[(size_t)b * D * D + i * D + j] - Lr[i * D + j]) / fmax(1.0, fabs(Lr[i * D + j])));
+        }
+        worstld = fmax(worstld, fabs(ld[b] - l2) / fabs(l2));
+    }
+    printf("vs fp64 Cholesky over %lld systems: max |dL| (rel. to max(1,|L|)) = %.3e, max rel. error of log det = %.3e\n",
+           (long long)Bcheck, worstL, worstld);
+    // ---- timing (no L output)
+    const int grid = sms * (occ > 0 ? occ : 1);
+    chol64_tc_kernel<<<grid, 128>>>(Btime, K, dP2, dp, nullptr, dld, dst);
+    cudaEvent_t a, c;
+    cudaEventCreate(&a); cudaEventCreate(&c);
+    cudaEventRecord(a);
+    for (int r = 0; r < 3; ++r) chol64_tc_kernel<<<grid, 128>>>(Btime, K, dP2, dp, nullptr, dld, dst);
+    cudaEventRecord(c);
+    e = cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, c);
+    ms /= 3;
+    cudaMemcpy(&st, dst, 4, cudaMemcpyDeviceToHost);
+    const double rate = (double)Btime / (ms * 1e-3);
+    printf("timing: cuda=%s status=%d  %lld systems in %.3f ms -> %.4g systems/s; factorisation flops D^3/3 -> %.2f TFLOP/s (%.1f %% of the "
+           "74.45 TFLOP/s FP32 peak); cycles per system per SM at 1.9 GHz: %.0f\n",
+           cudaGetErrorString(e), st, (long long)Btime, ms, rate, rate * (64.0 * 64 * 64 / 3) / 1e12,
+           rate * (64.0 * 64 * 64 / 3) / 74.45e12 * 100, 1.9e9 * sms / rate);
+    return 0;
+}
