@@ -224,6 +224,7 @@ int main(int argc, char** argv) {
     cudaMemset(dst, 0, 4);
     cudaMemset(dL, 0, (size_t)Bcheck * D * D * 4);
     int occ = 0, sms = 148;
+    cudaFuncSetAttribute(chol64_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);     // 8 CTAs x 18.7 KB per SM
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, chol64_tc_kernel, 128, 0);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     printf("chol64_tc: occupancy %d CTAs/SM (x2 systems each), %d SMs\n", occ, sms);
