@@ -26,7 +26,10 @@ namespace cg = cooperative_groups;
 
 namespace vmp {
 
-constexpr int SM_THREADS = 256;
+constexpr int SM_THREADS_F32 = 512;         // fp32: <= 128 registers per thread
+constexpr int SM_THREADS_F64 = 256;
+template <typename T> struct SmThreads { static constexpr int value = SM_THREADS_F64; };
+template <> struct SmThreads<float> { static constexpr int value = SM_THREADS_F32; };
 constexpr int SM_MAX_PAIRS_PER_CTA = 1024;
 constexpr int SM_MAX_K = 32;
 
@@ -196,7 +199,7 @@ __device__ void small_theta_record_student(int k, int K, const T* __restrict__ a
 
 // ---- the step -------------------------------------------------------------------------------------------------------------
 template <typename T, int D>
-__global__ void __launch_bounds__(SM_THREADS) svae_small_step_kernel(const SmallStepParams<T> p) {
+__global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(const SmallStepParams<T> p) {
     using PM = PairMath<T, D>;
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
@@ -376,9 +379,11 @@ template <typename T> size_t small_step_smem(int K, int D, int ppc) {
 template <typename T, int D>
 static int launch_small_step(SmallStepParams<T> p, cudaStream_t st) {
     const int64_t pairs = (int64_t)p.N * p.K;
-    p.split = p.S < 4 ? p.S : 4;
+    constexpr int THREADS = SmThreads<T>::value;
+    p.split = p.S < 8 ? p.S : 8;
+    while (p.split > 1 && pairs * p.split > (int64_t)16 * THREADS * 2) --p.split;      // at most ~2 work items per thread
     int C = 1;
-    while (C < 16 && pairs * p.split > (int64_t)C * SM_THREADS) C *= 2;    // about one work item per thread, at most 16 CTAs
+    while (C < 16 && pairs * p.split > (int64_t)C * THREADS) C *= 2;       // about one work item per thread, at most 16 CTAs
     if ((int64_t)((p.N + C - 1) / C) * p.K > SM_MAX_PAIRS_PER_CTA) return -100;
     p.ppc = (p.N + C - 1) / C;
     const size_t smem = small_step_smem<T>(p.K, D, p.ppc);
@@ -394,7 +399,7 @@ static int launch_small_step(SmallStepParams<T> p, cudaStream_t st) {
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C, 1, 1);
-    cfg.blockDim = dim3(SM_THREADS, 1, 1);
+    cfg.blockDim = dim3(THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];

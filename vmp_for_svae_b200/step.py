@@ -190,6 +190,12 @@ def svae_step_host(phi_enc_host, phi_gmm, theta, prior, rho, stepper, seed=0, st
     if copy_back is not None:
         copy_back[0].copy_(st.log_r, non_blocking=True)
         copy_back[1].copy_(st.x_sample, non_blocking=True)
-    theta_h = [t.to('cpu') for t in theta]
+    # one packed device buffer -> ONE device-to-host copy for the five global parameters (each .to('cpu') is a synchronising
+    # copy of its own; at the launch-bound shapes that is most of the end-to-end time)
+    flat = torch.cat([t.reshape(-1) for t in theta]).to('cpu')
+    theta_h, o = [], 0
+    for t in theta:
+        theta_h.append(flat[o:o + t.numel()].reshape(t.shape))
+        o += t.numel()
     elbo = out['elbo_acc'].to('cpu', non_blocking=False)
     return elbo.numpy(), theta_h
