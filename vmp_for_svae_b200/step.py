@@ -43,7 +43,7 @@ class SVAEStep(object):
         self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)   # ticket counter of the fused NG tail
         # launch-bound shapes on one GPU (C1 / C2): the whole step is ONE kernel on a thread-block cluster
         self.single_launch = (not self.use_dist) and core.small_step_supported(self.N, K, D)
-        self._bound = None
+        self._bound, self._bound_calls = None, 0
 
     def step(self, phi_enc, phi_gmm, theta, prior, rho, seed=0, noise=None, u=None, only_alpha=False,
              kernel_events=None):
@@ -54,14 +54,20 @@ class SVAEStep(object):
             pr, to = ([prior[0]], [theta[0]]) if only_alpha else (prior, theta)
             b = self._bound
             if b is not None:
-                k = b.key                     # same tensors as last time?  (theta is updated in place: a loop binds once)
+                # same tensor OBJECTS as last time?  (theta is updated in place: a loop binds once.)  The bound call keeps
+                # references to its tensors, so an id() cannot be recycled while it is bound; storage swaps are caught by
+                # re-checking the data pointers every 64th call.
                 ts = (eta1, eta2_diag) + tuple(phi_gmm) + tuple(theta) + tuple(pr) + tuple(to)
-                if len(k) != len(ts) or any(t.data_ptr() != q for t, q in zip(ts, k)) or b.only_alpha != bool(only_alpha):
+                ids = tuple(map(id, ts))
+                self._bound_calls += 1
+                if ids != b.ids or b.only_alpha != bool(only_alpha) or \
+                        ((self._bound_calls & 63) == 0 and tuple(t.data_ptr() for t in ts) != b.key):
                     b = None
             if b is None:
                 b = core.BoundSmallStep(eta1, eta2_diag, phi_gmm, theta, pr, to, self.S, self.den_mode, only_alpha, self.log_r,
                                         self.x_sample, self.z, self.stats, self.elbo_acc, point_offset=self.point_offset)
                 b.only_alpha = bool(only_alpha)
+                b.ids = tuple(map(id, (eta1, eta2_diag) + tuple(phi_gmm) + tuple(theta) + tuple(pr) + tuple(to)))
                 self._bound = b
             if noise is not None:
                 noise = core._chk(noise, (self.N, self.K, self.D, self.S), self.dtype, 'noise')
