@@ -128,6 +128,29 @@ int vmp_svae_small_step_f64(int64_t N, int K, int D, int S, int den_mode, int on
                             int64_t point_offset, double* log_r, double* x_sample, int32_t* z, double* x_k_samples,
                             double* stats, double* elbo_acc, void* stream);
 
+/* The same call with its arguments in one struct (dtype: 0 = f32, 1 = f64; pointers as in vmp_svae_small_step_*): a host
+ * language binding fills the struct ONCE per set of buffers and only rewrites rho / seed per step — at the launch-bound shapes
+ * the per-argument marshalling of a 32-argument FFI call costs as much as the kernel.                                     */
+typedef struct VmpSmallStepArgs {
+    int64_t N;
+    int32_t K, D, S, den_mode, only_alpha, dtype;
+    const void *eta1, *eta2_diag, *eta1_phi2, *L_raw, *pi_raw;
+    const void* theta[5];
+    const void* prior[5];
+    void* theta_out[5];
+    double rho;
+    const double* rho_dev;
+    const void *noise, *gumbel_u;
+    uint64_t seed;
+    int64_t point_offset;
+    void *log_r, *x_sample;
+    int32_t* z;
+    void* x_k_samples;
+    double *stats, *elbo_acc;
+    void* stream;
+} VmpSmallStepArgs;
+int vmp_svae_small_step_packed(const VmpSmallStepArgs* args);
+
 /* ---- reverse pass of the fused local step ---------------------------------------------------------------
  * Replaces what TF's autodiff builds for opt.compute_gradients(-elbo) (experiments.py:232) through svae.e_step
  * (svae.py:39-100), the per-component sampling (svae.py:103-123) and the regulariser of compute_elbo / compute_elbo_smm

@@ -51,10 +51,22 @@ _SIGS = {
     'vmp_mixture_fit_workspace_bytes': [c_int, c_int],
     'vmp_mixture_record_len': [c_int],
     'vmp_svae_small_step_supported': [c_i64, c_int, c_int],
+    'vmp_svae_small_step_packed': [c_ptr],
     'vmp_mixture_estep_fused_f32': [c_i64, c_int, c_int, c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_int, c_ptr],
     'vmp_fma_probe': [c_int, c_int, c_int, c_ptr, c_ptr],
 }
 EXPORTS = sorted([n for n in _SIGS] + [n + s for n in _SIGS_T for s in ('_f32', '_f64')])
+
+
+class SmallStepArgs(ctypes.Structure):
+    """VmpSmallStepArgs of include/vmp_svae.h"""
+    _fields_ = [('N', c_i64), ('K', ctypes.c_int32), ('D', ctypes.c_int32), ('S', ctypes.c_int32), ('den_mode', ctypes.c_int32),
+                ('only_alpha', ctypes.c_int32), ('dtype', ctypes.c_int32),
+                ('eta1', c_ptr), ('eta2_diag', c_ptr), ('eta1_phi2', c_ptr), ('L_raw', c_ptr), ('pi_raw', c_ptr),
+                ('theta', c_ptr * 5), ('prior', c_ptr * 5), ('theta_out', c_ptr * 5),
+                ('rho', c_dbl), ('rho_dev', c_ptr), ('noise', c_ptr), ('gumbel_u', c_ptr), ('seed', c_u64),
+                ('point_offset', c_i64), ('log_r', c_ptr), ('x_sample', c_ptr), ('z', c_ptr), ('x_k_samples', c_ptr),
+                ('stats', c_ptr), ('elbo_acc', c_ptr), ('stream', c_ptr)]
 
 
 class VmpError(RuntimeError):

@@ -171,26 +171,39 @@ class BoundSmallStep(object):
         self.key = tuple(t.data_ptr() for t in tensors)
         self.keep = tensors                                   # the bound tensors must stay alive
         self.N, self.K, self.D, self.S, self.dt, self.dev = N, K, D, int(S), dt, dev
-        self.fn = getattr(_lib.load(), 'vmp_svae_small_step' + _lib.suffix(dt))
-        self.arrs = (_ptr_array(theta, 5), _ptr_array(prior, 5), _ptr_array(theta_out, 5))
-        self.head = (N, K, D, int(S), int(den_mode), int(bool(only_alpha)), ptr(eta1), ptr(eta2_diag), ptr(phi_gmm[0]),
-                     ptr(phi_gmm[1]), ptr(phi_gmm[2])) + self.arrs
-        self.tail = (ptr(log_r), ptr(x_sample), ptr(z), None, ptr(stats), ptr(elbo_acc))
-        self.point_offset = int(point_offset)
+        self.fn = _lib.load().vmp_svae_small_step_packed
+        a = _lib.SmallStepArgs()
+        a.N, a.K, a.D, a.S, a.den_mode, a.only_alpha = N, K, D, int(S), int(den_mode), int(bool(only_alpha))
+        a.dtype = 0 if dt == torch.float32 else 1
+        a.eta1, a.eta2_diag = eta1.data_ptr(), eta2_diag.data_ptr()
+        a.eta1_phi2, a.L_raw, a.pi_raw = phi_gmm[0].data_ptr(), phi_gmm[1].data_ptr(), phi_gmm[2].data_ptr()
+        for i, t in enumerate(theta):
+            a.theta[i] = t.data_ptr()
+        for i, t in enumerate(prior):
+            a.prior[i] = t.data_ptr()
+        for i, t in enumerate(theta_out):
+            a.theta_out[i] = t.data_ptr()
+        a.point_offset = int(point_offset)
+        a.log_r, a.x_sample, a.z = log_r.data_ptr(), x_sample.data_ptr(), z.data_ptr()
+        a.stats, a.elbo_acc = stats.data_ptr(), elbo_acc.data_ptr()
+        self.args, self.ref = a, ctypes.byref(a)
         self.out = dict(log_r=log_r, x_sample=x_sample, z=z, x_k_samples=None, elbo_acc=elbo_acc, stats=stats)
-        self.same_device = dev.index is None or dev.index == torch.cuda.current_device()
 
     def __call__(self, rho, seed=0, noise=None, u=None):
-        rho_dev = None
+        a = self.args
         if isinstance(rho, torch.Tensor):
-            rho_dev, rho = ptr(rho), 0.0
-        args = self.head + (float(rho), rho_dev, ptr(noise), ptr(u), int(seed) & 0xFFFFFFFFFFFFFFFF, self.point_offset) + \
-            self.tail + (stream_ptr(self.dev),)
-        if self.same_device and (self.dev.index is None or self.dev.index == torch.cuda.current_device()):
-            rc = self.fn(*args)
+            a.rho_dev, a.rho = rho.data_ptr(), 0.0
+        else:
+            a.rho_dev, a.rho = None, rho
+        a.noise = noise.data_ptr() if noise is not None else None
+        a.gumbel_u = u.data_ptr() if u is not None else None
+        a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        a.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if self.dev.index is None or self.dev.index == torch.cuda.current_device():
+            rc = self.fn(self.ref)
         else:
             with torch.cuda.device(self.dev):
-                rc = self.fn(*args)
+                rc = self.fn(self.ref)
         if rc != 0:
             raise (ValueError if rc < 0 else _lib.VmpError)('vmp_svae_small_step: status %d' % rc)
         return self.out

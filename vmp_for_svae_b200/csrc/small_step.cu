@@ -476,4 +476,22 @@ int vmp_svae_small_step_f64(int64_t N, int K, int D, int S, int den_mode, int on
                                                 x_sample, z, x_k_samples, stats, elbo_acc, stream);
     return rc == -100 ? VMP_E_BADARG : rc;
 }
+int vmp_svae_small_step_packed(const VmpSmallStepArgs* a) {
+    if (!a) return VMP_E_BADARG;
+    if (a->dtype == 0)
+        return vmp_svae_small_step_f32(a->N, a->K, a->D, a->S, a->den_mode, a->only_alpha, (const float*)a->eta1,
+                                       (const float*)a->eta2_diag, (const float*)a->eta1_phi2, (const float*)a->L_raw,
+                                       (const float*)a->pi_raw, (const float* const*)a->theta, (const float* const*)a->prior,
+                                       (float* const*)a->theta_out, a->rho, a->rho_dev, (const float*)a->noise,
+                                       (const float*)a->gumbel_u, a->seed, a->point_offset, (float*)a->log_r, (float*)a->x_sample,
+                                       a->z, (float*)a->x_k_samples, a->stats, a->elbo_acc, a->stream);
+    if (a->dtype == 1)
+        return vmp_svae_small_step_f64(a->N, a->K, a->D, a->S, a->den_mode, a->only_alpha, (const double*)a->eta1,
+                                       (const double*)a->eta2_diag, (const double*)a->eta1_phi2, (const double*)a->L_raw,
+                                       (const double*)a->pi_raw, (const double* const*)a->theta, (const double* const*)a->prior,
+                                       (double* const*)a->theta_out, a->rho, a->rho_dev, (const double*)a->noise,
+                                       (const double*)a->gumbel_u, a->seed, a->point_offset, (double*)a->log_r,
+                                       (double*)a->x_sample, a->z, (double*)a->x_k_samples, a->stats, a->elbo_acc, a->stream);
+    return VMP_E_BADMODE;
+}
 }
