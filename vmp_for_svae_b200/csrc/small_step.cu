@@ -215,6 +215,8 @@ __global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(co
     T* tden = tnum + (size_t)ppc * K;                                 // [ppc*K]
     T* x0 = tden + (size_t)ppc * K;                                   // [ppc*K][D] first sample of every pair
     T* xs = x0 + (size_t)ppc * K * D;                                 // [ppc][D]   selected samples
+    T* gum = xs + (size_t)ppc * D;                                    // [ppc*K]   Gumbel noise of the categorical draw
+    T* rr = gum + (size_t)ppc * K;                                    // [ppc*K]   responsibilities
     __shared__ double red[32];
     const int tid = threadIdx.x;
 
@@ -281,6 +283,8 @@ __global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(co
         if (sp == 0) {
             sc[q] = pm.score;
             snum += T(S) * (pm.hld - T(0.5 * VMP_LOG_2PI) * T(D));
+            const T u = p.gum_u != nullptr ? p.gum_u[pair] : (T)philox_uniform_pair(p.seed, gpair);
+            gum[q] = gumbel_from_uniform<T>(u);                      // the draw's noise is per pair: no need to serialise it per point
         }
         atomicAdd(&tnum[q], snum / T(S));
         atomicAdd(&tden[q], sden / T(S));
@@ -301,9 +305,8 @@ __global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(co
             const T lr = s[k] - lse;
             s[k] = lr;
             p.log_r[n * K + k] = lr;
-            const uint64_t pair = (uint64_t)n * K + k;
-            const T u = p.gum_u != nullptr ? p.gum_u[pair] : (T)philox_uniform_pair(p.seed, pair + p.pair_offset);
-            const T cand = lr + gumbel_from_uniform<T>(u);
+            rr[(size_t)pl * K + k] = t_exp(lr);
+            const T cand = lr + gum[(size_t)pl * K + k];
             if (cand > best) { best = cand; zb = k; }
         }
         if (p.z != nullptr) p.z[n] = zb;
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(co
     // ELBO partials of this CTA
     double e_num = 0.0, e_den = 0.0;
     for (int q = tid; q < npairs; q += blockDim.x) {
-        const double r = (double)t_exp(sc[q]);
+        const double r = (double)rr[q];
         e_num += r * ((double)tnum[q] + (double)sc[q]);
         e_den += r * (double)tden[q];
     }
@@ -329,13 +332,13 @@ __global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(co
         const int k = e / SL, j = e - k * SL;
         double acc = 0.0;
         if (j < 2) {
-            for (int pl = 0; pl < npts; ++pl) acc += (double)t_exp(sc[(size_t)pl * K + k]);
+            for (int pl = 0; pl < npts; ++pl) acc += (double)rr[(size_t)pl * K + k];
         } else if (j < 2 + D) {
-            for (int pl = 0; pl < npts; ++pl) acc += (double)t_exp(sc[(size_t)pl * K + k]) * (double)xs[(size_t)pl * D + (j - 2)];
+            for (int pl = 0; pl < npts; ++pl) acc += (double)rr[(size_t)pl * K + k] * (double)xs[(size_t)pl * D + (j - 2)];
         } else {
             const int a = (j - 2 - D) / D, b2 = (j - 2 - D) - a * D;
             for (int pl = 0; pl < npts; ++pl)
-                acc += (double)t_exp(sc[(size_t)pl * K + k]) * (double)xs[(size_t)pl * D + a] * (double)xs[(size_t)pl * D + b2];
+                acc += (double)rr[(size_t)pl * K + k] * (double)xs[(size_t)pl * D + a] * (double)xs[(size_t)pl * D + b2];
         }
         sstat[e] = acc;
     }
@@ -343,8 +346,12 @@ __global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(co
     // ---------------- phase 4: reduce over the cluster through DSMEM, store, natural-gradient update of this CTA's slice
     const double rho = p.rho_dev != nullptr ? *p.rho_dev : p.rho;
     for (int e = tid + crank * (int)blockDim.x; e < K * SL; e += C * (int)blockDim.x) {
+        double part[16];                                           // all remote reads in flight at once (DSMEM latency ~200 cycles each)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) part[c] = c < C ? cluster.map_shared_rank(sstat, c)[e] : 0.0;
         double tot = 0.0;
-        for (int c = 0; c < C; ++c) tot += cluster.map_shared_rank(sstat, c)[e];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) tot += part[c];
         p.stats[e] = tot;
         const int k = e / SL, j = e - k * SL;
         if (j == 0) {
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(SmThreads<T>::value) svae_small_step_kernel(co
 
 template <typename T> size_t small_step_smem(int K, int D, int ppc) {
     const int PL = D * D + 2 * D + 4, TL = D * D + D + 4, SL = D * D + D + 2;
-    return sizeof(double) * ((size_t)K * SL + 4) + sizeof(T) * ((size_t)K * (PL + TL) + (size_t)ppc * K * (3 + D) + (size_t)ppc * D) + 16;
+    return sizeof(double) * ((size_t)K * SL + 4) + sizeof(T) * ((size_t)K * (PL + TL) + (size_t)ppc * K * (5 + D) + (size_t)ppc * D) + 16;
 }
 
 template <typename T, int D>
