@@ -396,13 +396,19 @@ static int launch_small_step(SmallStepParams<T> p, cudaStream_t st) {
     const size_t smem = small_step_smem<T>(p.K, D, p.ppc);
     if (smem > 200 * 1024) return -100;
     auto kern = svae_small_step_kernel<T, D>;
-    if (smem > 48 * 1024) {
+    // function attributes are set once per instantiation (and again only if a larger size is needed): at these shapes every
+    // extra runtime call is a measurable part of the step
+    static size_t smem_set = 0;
+    static bool nonportable_set = false;
+    if (smem > 48 * 1024 && smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+        smem_set = smem;
     }
-    if (C > 8) {                                                            // 16 CTAs: non-portable cluster size
+    if (C > 8 && !nonportable_set) {                                        // 16 CTAs: non-portable cluster size
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return (int)e;
+        nonportable_set = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(C, 1, 1);
@@ -417,7 +423,7 @@ static int launch_small_step(SmallStepParams<T> p, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
-    return e == cudaSuccess ? launch_status() : (int)e;
+    return (int)e;                                                          // launch errors are returned by the launch call itself
 }
 
 template <typename T>
