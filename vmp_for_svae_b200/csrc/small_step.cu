@@ -32,6 +32,9 @@ template <typename T> struct SmThreads { static constexpr int value = SM_THREADS
 template <> struct SmThreads<float> { static constexpr int value = SM_THREADS_F32; };
 constexpr int SM_MAX_PAIRS_PER_CTA = 1024;
 constexpr int SM_MAX_K = 32;
+#ifndef SM_MAX_CLUSTER
+#define SM_MAX_CLUSTER 16
+#endif
 
 template <typename T> struct SmallStepParams {
     int N, K, S, den_mode, only_alpha, ppc, split;   // ppc: points per CTA; split: threads sharing the S samples of a pair
@@ -390,7 +393,7 @@ static int launch_small_step(SmallStepParams<T> p, cudaStream_t st) {
     p.split = p.S < 8 ? p.S : 8;
     while (p.split > 1 && pairs * p.split > (int64_t)16 * THREADS * 2) --p.split;      // at most ~2 work items per thread
     int C = 1;
-    while (C < 16 && pairs * p.split > (int64_t)C * THREADS) C *= 2;       // about one work item per thread, at most 16 CTAs
+    while (C < SM_MAX_CLUSTER && pairs * p.split > (int64_t)C * THREADS) C *= 2;       // about one work item per thread
     if ((int64_t)((p.N + C - 1) / C) * p.K > SM_MAX_PAIRS_PER_CTA) return -100;
     p.ppc = (p.N + C - 1) / C;
     const size_t smem = small_step_smem<T>(p.K, D, p.ppc);
