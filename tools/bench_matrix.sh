@@ -7,10 +7,10 @@ mkdir -p gpurun_out
 for w in $WL; do
   steps=30; [ "$w" = "c5" ] && steps=2
   if [ "$N" = "1" ]; then
-    timeout 600 python bench.py --workload $w --steps $steps --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_${w}_${N}gpu.json 2> gpurun_out/r2_bench_${w}_${N}gpu.err
+    timeout 600 python bench.py --workload $w --steps $steps --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_${w}_${N}gpu.json 2> gpurun_out/r2_bench_${w}_${N}gpu.err
   else
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 \
-      bench.py --gpus $N --workload $w --steps $steps --warmup 5 --no-cpu-baseline > gpurun_out/r2_bench_${w}_${N}gpu.json 2> gpurun_out/r2_bench_${w}_${N}gpu.err
+      bench.py --gpus $N --workload $w --steps $steps --warmup 3 --no-cpu-baseline > gpurun_out/r2_bench_${w}_${N}gpu.json 2> gpurun_out/r2_bench_${w}_${N}gpu.err
   fi
   python - <<PY
 import json
