@@ -56,6 +56,11 @@ template <int D, int BS_> struct FastGeom {
     static constexpr int LD = D + 4;                 // padded row stride of the staged matrices
     static constexpr int REC = 2 * D * LD + 2 * D + 8;
     static constexpr int TS = BS + 4;                // transpose tile stride
+    // Lane numbering inside a warp (profiles/r2_smem_lane_bits.md): a 128-bit shared-memory load costs 4 wavefronts when the
+    // four lanes of an aligned quad read four different chunks (address selected by lane bits b0 AND b1) and 2 otherwise.
+    // The staged P2 / W rows are selected by gl, the column broadcasts by the pair; so gl must not occupy both b0 and b1, and
+    // neither may the pair index.  GLMASK = the lane-id bits that hold gl (low to high); the remaining bits hold the pair.
+    static constexpr unsigned GLMASK = BS_ == 16 ? 0x1eu : BS_ == 8 ? 0x0du : 0x05u;
     // group scratch: col[2][D] | vec[D] | ybf[max(BS,4)] | tbf[BS][TS] | mub[D] | p1b[D] | xb[D] | ab[D] | ib[D]; kept congruent to BS
     // mod 32 so the groups of one warp land in different banks.  mub / p1b / xb hold per-point state (mu1, p1, the
     // running arg-max sample) that would otherwise pin 12 registers across the whole factorisation.
@@ -157,19 +162,36 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return r;
 }
 
-template <int BS> __device__ __forceinline__ float group_sum(float v) {
+// scatter the low bits of v to the set bits of mask / gather them back (compile-time when v is a constant)
+__host__ __device__ constexpr unsigned bits_deposit(unsigned v, unsigned mask) {
+    unsigned r = 0;
+    for (unsigned b = 0, k = 0; b < 32; ++b)
+        if (mask >> b & 1u) r |= ((v >> k++) & 1u) << b;
+    return r;
+}
+__host__ __device__ constexpr unsigned bits_extract(unsigned v, unsigned mask) {
+    unsigned r = 0;
+    for (unsigned b = 0, k = 0; b < 32; ++b)
+        if (mask >> b & 1u) r |= ((v >> b) & 1u) << k++;
+    return r;
+}
+// reductions over the lanes of one pair: butterflies over the lane bits that hold gl
+template <unsigned GLMASK> __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int o = BS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, BS);
+    for (int b = 4; b >= 0; --b)
+        if (GLMASK >> b & 1u) v += __shfl_xor_sync(0xffffffffu, v, 1 << b);
     return v;
 }
-template <int BS> __device__ __forceinline__ double group_sum_d(double v) {
+template <unsigned GLMASK> __device__ __forceinline__ double group_sum_d(double v) {
 #pragma unroll
-    for (int o = BS / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, BS);
+    for (int b = 4; b >= 0; --b)
+        if (GLMASK >> b & 1u) v += __shfl_xor_sync(0xffffffffu, v, 1 << b);
     return v;
 }
-template <int BS> __device__ __forceinline__ float group_max(float v) {
+template <unsigned GLMASK> __device__ __forceinline__ float group_max(float v) {
 #pragma unroll
-    for (int o = BS / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o, BS));
+    for (int b = 4; b >= 0; --b)
+        if (GLMASK >> b & 1u) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1 << b));
     return v;
 }
 
@@ -190,9 +212,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ double cta_acc[4];
 
+    constexpr unsigned GLMASK = G::GLMASK;
+    static_assert(bits_extract(GLMASK, GLMASK) == BS - 1, "GLMASK must have log2(BS) bits");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int gl = lane % BS;
-    const int grp = warp * GPW + lane / BS;
+    const int gl = (int)bits_extract((unsigned)lane, GLMASK);
+    const int lane_pair = lane & (int)(~GLMASK & 31u);        // this lane's pair bits: | bits_deposit(l, GLMASK) = lane of group-lane l
+    const int grp = warp * GPW + (int)bits_extract((unsigned)lane, ~GLMASK & 31u);
+    auto group_bcast = [&](float v, int l) { return __shfl_sync(FULL, v, lane_pair | (int)bits_deposit((unsigned)l, GLMASK)); };
     float* col = gsm + grp * GS;          // [2][D]
     float* vec = col + 2 * D;             // [D]
     float* ybf = vec + D;                 // [BS]
@@ -317,12 +343,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             static_for<0, D>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 constexpr int rj = j / BS, lj = j % BS;
-                const float piv = __shfl_sync(FULL, A[rj][j], lj, BS);
+                const float piv = group_bcast(A[rj][j], lj);
                 float inv = rsqrt_approx(piv);                           // bare MUFU.RSQ (pivots are O(1): no denormals)
                 inv = inv * fmaf(-0.5f * piv * inv, inv, 1.5f);          // one Newton step: ~0.5 ulp
                 hl2 += lg2_approx(piv);                                  // bare MUFU.LG2 (rel. error 2^-22; NaN flags a bad pivot)
-                const float yj = __shfl_sync(FULL, g[rj] * inv, lj, BS);
-                const float y1j = __shfl_sync(FULL, g1[rj] * inv, lj, BS);
+                const float yj = group_bcast(g[rj] * inv, lj);
+                const float y1j = group_bcast(g1[rj] * inv, lj);
                 q = fmaf(yj, y1j, q);
                 // a_j and 1/L_jj go to shared memory (frees 8 registers); both are group-uniform, so four columns are
                 // batched into one 128-bit store each by lane 0 (6 fewer wavefronts per 4 columns than scalar stores)
@@ -417,7 +443,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
 #pragma unroll
                     for (int i = BS - 1; i >= 0; --i) {
                         const float t = tbf[i * TS + gl];               // L[rb*BS+i][rb*BS+gl]
-                        const float yi = __shfl_sync(FULL, w[rb] * idg[rb], i, BS);
+                        const float yi = group_bcast(w[rb] * idg[rb], i);
                         y[rb] = (gl == i) ? yi : y[rb];
                         w[rb] = fmaf(-t, yi, w[rb]);
                     }
@@ -474,8 +500,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     const float t = (t0 + t1) + (t2 + t3);
                     q2 = fmaf(t, t, q2);
                 });
-                e2 = group_sum<BS>(e2);
-                q2 = group_sum<BS>(q2);
+                e2 = group_sum<GLMASK>(e2);
+                q2 = group_sum<GLMASK>(q2);
                 snum += -0.5f * e2;
                 sden += (p.den_mode == VMP_DEN_GAUSS) ? (scl[2] - 0.5f * q2)
                                                       : (scl[2] - 0.5f * (scl[3] + (float)Dr) * log1pf(q2 / scl[3]));
@@ -501,10 +527,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
         __syncwarp();
         float mx = -CUDART_INF_F;
         for (int k = gl; k < K; k += BS) mx = fmaxf(mx, kst[3 * k]);
-        mx = group_max<BS>(mx);
+        mx = group_max<GLMASK>(mx);
         double se = 0.0;
         for (int k = gl; k < K; k += BS) se += (double)expf(kst[3 * k] - mx);
-        se = group_sum_d<BS>(se);
+        se = group_sum_d<GLMASK>(se);
         const float lse = mx + (float)log(se);
         double en = 0.0, ed = 0.0;
         if (active) {
@@ -522,8 +548,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             }
             if (p.z != nullptr && gl == 0) p.z[n] = zbest;
         }
-        en = group_sum_d<BS>(en);
-        ed = group_sum_d<BS>(ed);
+        en = group_sum_d<GLMASK>(en);
+        ed = group_sum_d<GLMASK>(ed);
         if (gl == 0 && active) {
             atomicAdd(&cta_acc[0], en);
             atomicAdd(&cta_acc[1], ed);
