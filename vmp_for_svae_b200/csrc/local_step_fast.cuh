@@ -430,45 +430,106 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     idg[r] = ib[r * BS + gl];
                     y[r] = 0.f;
                 }
-                // back substitution, block rows from the bottom
-                static_for_down<ROWS>([&](auto rbc) {
-                    constexpr int rb = decltype(rbc)::value;
-                    __syncwarp();
+                // back substitution L^T y = w, block rows from the bottom
+                if constexpr (BS == 4) {
+                    // Row-owner form without any transposition: the owner of row R, once y_R is known, adds L[R][c] y_R to its
+                    // PRIVATE partial sums pw[c], c < R; a block of four columns is completed by a reduce-scatter over the
+                    // four lanes of the pair (3 shuffles) when the sweep reaches it, the in-block terms by 5 more.  No shared
+                    // memory: the 36 (D=32) / 10 (D=16) 4x4 block transposes of the tile form were ~22 % of this engine's
+                    // shared-memory wavefronts.
+                    constexpr int HI = 31 - __builtin_clz(GLMASK), LO = __builtin_ctz(GLMASK);   // lane bits of gl bit 1 / bit 0
+                    const bool ghi = (gl & 2) != 0, glo = (gl & 1) != 0;
+                    float pw[D - BS];
 #pragma unroll
-                    for (int q4 = 0; q4 < BS / 4; ++q4)
-                        reinterpret_cast<float4*>(tbf + gl * TS)[q4] =
-                            make_float4(A[rb][rb * BS + 4 * q4], A[rb][rb * BS + 4 * q4 + 1], A[rb][rb * BS + 4 * q4 + 2],
-                                        A[rb][rb * BS + 4 * q4 + 3]);
-                    __syncwarp();
+                    for (int c = 0; c < D - BS; ++c) pw[c] = 0.f;
+                    static_for_down<ROWS>([&](auto rbc) {
+                        constexpr int rb = decltype(rbc)::value;
+                        float wv = w[rb];
+                        if constexpr (rb < ROWS - 1) {
+                            // lane gl <- sum over the four lanes of pw[rb*4 + gl]
+                            const float s0 = ghi ? pw[rb * 4 + 0] : pw[rb * 4 + 2], s1 = ghi ? pw[rb * 4 + 1] : pw[rb * 4 + 3];
+                            float k0 = ghi ? pw[rb * 4 + 2] : pw[rb * 4 + 0], k1 = ghi ? pw[rb * 4 + 3] : pw[rb * 4 + 1];
+                            k0 += __shfl_xor_sync(FULL, s0, 1 << HI);
+                            k1 += __shfl_xor_sync(FULL, s1, 1 << HI);
+                            const float s2 = glo ? k0 : k1;
+                            float kk = glo ? k1 : k0;
+                            kk += __shfl_xor_sync(FULL, s2, 1 << LO);
+                            wv -= kk;
+                        }
+                        // rows 3..0 of the block: lane i finishes y_i, its in-block terms L[i][c] y_i wait in pd[c], c < i
+                        float pd0 = 0.f, pd1 = 0.f, pd2 = 0.f;
+                        {   // i = 3
+                            const float ym = (gl == 3) ? wv * idg[rb] : 0.f;
+                            y[rb] = (gl == 3) ? ym : y[rb];
+                            pd2 = A[rb][rb * 4 + 2] * ym;
+                            pd1 = A[rb][rb * 4 + 1] * ym;
+                            pd0 = A[rb][rb * 4 + 0] * ym;
+                        }
+                        {   // i = 2: lane 2 needs pd2 of lane 3
+                            const float t = group_bcast(pd2, 3);
+                            const float ym = (gl == 2) ? (wv - t) * idg[rb] : 0.f;
+                            y[rb] = (gl == 2) ? ym : y[rb];
+                            pd1 = fmaf(A[rb][rb * 4 + 1], ym, pd1);
+                            pd0 = fmaf(A[rb][rb * 4 + 0], ym, pd0);
+                        }
+                        {   // i = 1: lane 1 needs pd1 of lanes 2 and 3 (lanes 0, 1 hold 0)
+                            float t = pd1 + __shfl_xor_sync(FULL, pd1, 1 << HI);
+                            t += __shfl_xor_sync(FULL, t, 1 << LO);
+                            const float ym = (gl == 1) ? (wv - t) * idg[rb] : 0.f;
+                            y[rb] = (gl == 1) ? ym : y[rb];
+                            pd0 = fmaf(A[rb][rb * 4 + 0], ym, pd0);
+                        }
+                        {   // i = 0
+                            float t = pd0 + __shfl_xor_sync(FULL, pd0, 1 << HI);
+                            t += __shfl_xor_sync(FULL, t, 1 << LO);
+                            if (gl == 0) y[rb] = (wv - t) * idg[rb];
+                        }
+                        // every lane now owns its y of this block row: its terms for all earlier columns
+                        if constexpr (rb > 0) {
 #pragma unroll
-                    for (int i = BS - 1; i >= 0; --i) {
-                        const float t = tbf[i * TS + gl];               // L[rb*BS+i][rb*BS+gl]
-                        const float yi = group_bcast(w[rb] * idg[rb], i);
-                        y[rb] = (gl == i) ? yi : y[rb];
-                        w[rb] = fmaf(-t, yi, w[rb]);
-                    }
-                    if constexpr (rb > 0) {
-                        ybf[gl] = -y[rb];                               // negated: the block updates become pure FMAs
-                        static_for<0, rb>([&](auto rb2c) {
-                            constexpr int rb2 = decltype(rb2c)::value;
-                            __syncwarp();
-#pragma unroll
-                            for (int q4 = 0; q4 < BS / 4; ++q4)
-                                reinterpret_cast<float4*>(tbf + gl * TS)[q4] =
-                                    make_float4(A[rb][rb2 * BS + 4 * q4], A[rb][rb2 * BS + 4 * q4 + 1],
-                                                A[rb][rb2 * BS + 4 * q4 + 2], A[rb][rb2 * BS + 4 * q4 + 3]);
-                            __syncwarp();
-                            float acc0 = w[rb2], acc1 = 0.f;
-#pragma unroll
-                            for (int i4 = 0; i4 < BS / 4; ++i4) {
-                                const float4 yv = reinterpret_cast<const float4*>(ybf)[i4];
-                                ffma2(acc0, acc1, tbf[(4 * i4 + 0) * TS + gl], tbf[(4 * i4 + 1) * TS + gl], yv.x, yv.y);
-                                ffma2(acc0, acc1, tbf[(4 * i4 + 2) * TS + gl], tbf[(4 * i4 + 3) * TS + gl], yv.z, yv.w);
-                            }
-                            w[rb2] = acc0 + acc1;
-                        });
-                    }
-                });
+                            for (int c = 0; c < rb * 4; c += 2) ffma2_bcast(pw[c], pw[c + 1], y[rb], A[rb][c], A[rb][c + 1]);
+                        }
+                    });
+                } else {
+                    static_for_down<ROWS>([&](auto rbc) {
+                        constexpr int rb = decltype(rbc)::value;
+                        __syncwarp();
+    #pragma unroll
+                        for (int q4 = 0; q4 < BS / 4; ++q4)
+                            reinterpret_cast<float4*>(tbf + gl * TS)[q4] =
+                                make_float4(A[rb][rb * BS + 4 * q4], A[rb][rb * BS + 4 * q4 + 1], A[rb][rb * BS + 4 * q4 + 2],
+                                            A[rb][rb * BS + 4 * q4 + 3]);
+                        __syncwarp();
+    #pragma unroll
+                        for (int i = BS - 1; i >= 0; --i) {
+                            const float t = tbf[i * TS + gl];               // L[rb*BS+i][rb*BS+gl]
+                            const float yi = group_bcast(w[rb] * idg[rb], i);
+                            y[rb] = (gl == i) ? yi : y[rb];
+                            w[rb] = fmaf(-t, yi, w[rb]);
+                        }
+                        if constexpr (rb > 0) {
+                            ybf[gl] = -y[rb];                               // negated: the block updates become pure FMAs
+                            static_for<0, rb>([&](auto rb2c) {
+                                constexpr int rb2 = decltype(rb2c)::value;
+                                __syncwarp();
+    #pragma unroll
+                                for (int q4 = 0; q4 < BS / 4; ++q4)
+                                    reinterpret_cast<float4*>(tbf + gl * TS)[q4] =
+                                        make_float4(A[rb][rb2 * BS + 4 * q4], A[rb][rb2 * BS + 4 * q4 + 1],
+                                                    A[rb][rb2 * BS + 4 * q4 + 2], A[rb][rb2 * BS + 4 * q4 + 3]);
+                                __syncwarp();
+                                float acc0 = w[rb2], acc1 = 0.f;
+    #pragma unroll
+                                for (int i4 = 0; i4 < BS / 4; ++i4) {
+                                    const float4 yv = reinterpret_cast<const float4*>(ybf)[i4];
+                                    ffma2(acc0, acc1, tbf[(4 * i4 + 0) * TS + gl], tbf[(4 * i4 + 1) * TS + gl], yv.x, yv.y);
+                                    ffma2(acc0, acc1, tbf[(4 * i4 + 2) * TS + gl], tbf[(4 * i4 + 3) * TS + gl], yv.z, yv.w);
+                                }
+                                w[rb2] = acc0 + acc1;
+                            });
+                        }
+                    });
+                }
                 // x = mu1 + y ; publish x - m_theta for the quadratic form
                 float x[ROWS];
                 __syncwarp();
