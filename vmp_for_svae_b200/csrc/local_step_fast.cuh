@@ -188,6 +188,26 @@ template <unsigned GLMASK> __device__ __forceinline__ double group_sum_d(double 
         if (GLMASK >> b & 1u) v += __shfl_xor_sync(0xffffffffu, v, 1 << b);
     return v;
 }
+// v[e] summed over the BS lanes of a pair, element e delivered to group-lane e (recursive halving: BS - 1 shuffles)
+template <int BS, unsigned GLMASK> __device__ __forceinline__ float group_reduce_scatter(float (&v)[BS], int gl) {
+    int n = BS;
+#pragma unroll
+    for (int bit = 31 - __builtin_clz((unsigned)BS) - 1; bit >= 0; --bit) {
+        const int half = n / 2;
+        const bool hb = (gl >> bit) & 1;
+        const int lanebit = (int)bits_deposit(1u << bit, GLMASK);
+#pragma unroll
+        for (int e = 0; e < BS / 2; ++e) {
+            if (e < half) {
+                const float send = hb ? v[e] : v[e + half];
+                const float keep = hb ? v[e + half] : v[e];
+                v[e] = keep + __shfl_xor_sync(0xffffffffu, send, lanebit);
+            }
+        }
+        n = half;
+    }
+    return v[0];
+}
 template <unsigned GLMASK> __device__ __forceinline__ float group_max(float v) {
 #pragma unroll
     for (int b = 4; b >= 0; --b)
@@ -493,6 +513,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 } else {
                     static_for_down<ROWS>([&](auto rbc) {
                         constexpr int rb = decltype(rbc)::value;
+                        if constexpr (rb < ROWS - 1) {
+                            // terms of the rows below for this block's columns: every lane multiplies its own rows (private
+                            // sums, lazy: only BS of them are live), then a reduce-scatter over the pair's lanes (BS - 1
+                            // shuffles) hands column rb*BS + gl to lane gl — instead of ROWS-1-rb tile transposes
+                            float pv[BS];
+#pragma unroll
+                            for (int e = 0; e < BS; ++e) pv[e] = 0.f;
+                            static_for<rb + 1, ROWS>([&](auto rsc) {
+                                constexpr int rs = decltype(rsc)::value;
+#pragma unroll
+                                for (int e = 0; e < BS; e += 2)
+                                    ffma2_bcast(pv[e], pv[e + 1], y[rs], A[rs][rb * BS + e], A[rs][rb * BS + e + 1]);
+                            });
+                            w[rb] -= group_reduce_scatter<BS, GLMASK>(pv, gl);
+                        }
                         __syncwarp();
     #pragma unroll
                         for (int q4 = 0; q4 < BS / 4; ++q4)
@@ -506,27 +541,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                             const float yi = group_bcast(w[rb] * idg[rb], i);
                             y[rb] = (gl == i) ? yi : y[rb];
                             w[rb] = fmaf(-t, yi, w[rb]);
-                        }
-                        if constexpr (rb > 0) {
-                            ybf[gl] = -y[rb];                               // negated: the block updates become pure FMAs
-                            static_for<0, rb>([&](auto rb2c) {
-                                constexpr int rb2 = decltype(rb2c)::value;
-                                __syncwarp();
-    #pragma unroll
-                                for (int q4 = 0; q4 < BS / 4; ++q4)
-                                    reinterpret_cast<float4*>(tbf + gl * TS)[q4] =
-                                        make_float4(A[rb][rb2 * BS + 4 * q4], A[rb][rb2 * BS + 4 * q4 + 1],
-                                                    A[rb][rb2 * BS + 4 * q4 + 2], A[rb][rb2 * BS + 4 * q4 + 3]);
-                                __syncwarp();
-                                float acc0 = w[rb2], acc1 = 0.f;
-    #pragma unroll
-                                for (int i4 = 0; i4 < BS / 4; ++i4) {
-                                    const float4 yv = reinterpret_cast<const float4*>(ybf)[i4];
-                                    ffma2(acc0, acc1, tbf[(4 * i4 + 0) * TS + gl], tbf[(4 * i4 + 1) * TS + gl], yv.x, yv.y);
-                                    ffma2(acc0, acc1, tbf[(4 * i4 + 2) * TS + gl], tbf[(4 * i4 + 3) * TS + gl], yv.z, yv.w);
-                                }
-                                w[rb2] = acc0 + acc1;
-                            });
                         }
                     });
                 }
