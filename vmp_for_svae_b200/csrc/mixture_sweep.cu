@@ -414,6 +414,199 @@ sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
     ng_tail_run<float>(tail, K, D, stats, gridDim.x);
 }
 
+// ---------------------------------------------------------------------------------------------------- S (tensor cores): D = 8
+// stats[k][f] = sum_n w[n][k] F[n][f] with F = the 45 products of the augmented row [x, 1] is a [K x N] x [N x 48] GEMM: legacy
+// warp-level mma.sync.m16n8k8 (tf32 operands split hi/lo, three MMAs per product: hi*hi + lo*hi + hi*lo, ~2^-21 relative per
+// term; the running fp32 sums are kept with FADDs and flushed to fp64 every SW_RUN points).  The contraction index is the point: one MMA step covers 8
+// points.  A fragment = w^T: the lane (g, t) loads r[n0+t][4g..4g+3] and r[n0+t+4][4g..4g+3] as two 128-bit rows (coalesced:
+// the eight g-lanes of a t cover one 128-byte row), output rows are assigned to components so that no shuffle is needed
+// (m-tile mt, row g -> component 4g + 2mt, row g+8 -> component 4g + 2mt + 1).  B fragment = the feature (slot 8q + g) of the
+// points t, t+4, gathered from the staged x rows with per-lane constant offsets (the constants 1 and 0 sit behind the rows).
+// 36 MMAs + ~150 other instructions per 8 points (the FP32 lane <-> component kernel: 600).  What then binds is memory-level
+// parallelism: every warp owns a ring of SWM_NST bulk-copy (cp.async.bulk + mbarrier) stages, one stage = the contiguous x, r
+// and u rows of a group of 8 points, issued three groups ahead by lane 0; groups are dealt to the warps in contiguous,
+// balanced chunks (runs of 256 points left 18 % of the warps idle in the last wave at N = 10^6).
+// d = a b (zero accumulator input)
+__device__ __forceinline__ void sw_mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ void sw_mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void sw_split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));        // the tensor core ignores the 13 low mantissa bits of lo
+}
+
+// per-warp ring of bulk-copy (TMA) stages: one stage = the x, r and u rows of one group of 8 points
+constexpr int SWM_NST = 4;                      // stages per warp: 3 groups (6.9 KB) in flight behind the one being multiplied
+constexpr int SWM_XA = 128;                     // x area: 64 floats of rows | 1, 0 at [64], [65] and again at [96], [97]
+constexpr int SWM_STAGE = SWM_XA + 2 * 8 * 32;  // floats per stage: x area | r rows (8 x K) | u rows (8 x K)
+constexpr int SWM_FLUSH = 32;                   // groups between two flushes of the fp32 sums (256 points)
+
+__device__ __forceinline__ uint32_t sw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sw_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void sw_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sw_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SW_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SW_DONE_%=;\n\t"
+        "bra SW_WAIT_%=;\n\t"
+        "SW_DONE_%=:\n\t}" ::"r"(sw_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void sw_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sw_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(sw_smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(SW_WARPS * 32, 2)
+sweep_stats_mma_kernel(int64_t N, int K, const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ u,
+                       double* __restrict__ stats, const NgTail tail) {
+    constexpr int D = 8, NA = sw_na(D), NT = 6;                     // 45 features in 6 n-tiles of 8 slots (3 spare = 0)
+    __shared__ double red[NA + 1][32];
+    __shared__ __align__(8) uint64_t bars[SW_WARPS][SWM_NST];
+    extern __shared__ __align__(128) float ring_raw[];               // [SW_WARPS][SWM_NST][SWM_STAGE]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    for (int e = threadIdx.x; e < (NA + 1) * 32; e += blockDim.x) (&red[0][0])[e] = 0.0;
+    float* ring = ring_raw + (size_t)wib * SWM_NST * SWM_STAGE;
+    for (int e = lane; e < SWM_NST * SWM_STAGE; e += 32) {           // stale rows of a partial last group must be finite
+        const int o = e % SWM_STAGE;
+        ring[e] = (o == 64 || o == 96) ? 1.f : 0.f;
+    }
+    if (lane < SWM_NST) sw_mbar_init(&bars[wib][lane], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the zero fill above precedes the bulk copies
+    __syncthreads();
+    // slot 8q + g -> (i, j) of the augmented lower triangle (e = i (i + 1) / 2 + j); index 8 = the constant 1, spare slots = 0 * 0.
+    // Offsets are relative to the row of point t (row t+4 is 32 floats further): the constants sit at [64 + d] and [96 + d].
+    int oi[NT], oj[NT];
+#pragma unroll
+    for (int q = 0; q < NT; ++q) {
+        const int e = 8 * q + g;
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        const int j = e - i * (i + 1) / 2;
+        oi[q] = e >= NA ? 65 - 8 * t : (i == 8 ? 64 - 8 * t : i);
+        oj[q] = e >= NA ? 65 - 8 * t : (j == 8 ? 64 - 8 * t : j);
+    }
+    // contiguous chunk of groups per warp (balanced to one group)
+    const int64_t G = (N + 7) / 8, nwarps = (int64_t)gridDim.x * SW_WARPS, gw = (int64_t)blockIdx.x * SW_WARPS + wib;
+    const int64_t per = (G + nwarps - 1) / nwarps, gbeg = min(G, gw * per), gend = min(G, gbeg + per);
+    const int64_t ng = gend - gbeg;
+    const bool kin = 4 * g < K, has_u = u != nullptr;
+    const uint32_t row_bytes = (uint32_t)K * 4u;
+    auto issue = [&](int64_t c) {                                    // lane 0: copies of group gbeg + c into stage c % NST
+        const int64_t n0 = (gbeg + c) * 8;
+        const uint32_t cnt = (uint32_t)min((int64_t)8, N - n0);
+        float* st = ring + (c % SWM_NST) * SWM_STAGE;
+        uint64_t* bar = &bars[wib][c % SWM_NST];
+        sw_mbar_expect_tx(bar, cnt * (32u + row_bytes * (has_u ? 2u : 1u)));
+        sw_bulk_g2s(st, x + n0 * D, cnt * 32u, bar);
+        sw_bulk_g2s(st + SWM_XA, r + n0 * K, cnt * row_bytes, bar);
+        if (has_u) sw_bulk_g2s(st + SWM_XA + 256, u + n0 * K, cnt * row_bytes, bar);
+    };
+    if (lane == 0)
+        for (int64_t c = 0; c < SWM_NST - 1 && c < ng; ++c) issue(c);
+    float acc[2][NT][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[m][q][c] = 0.f;
+    float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f), one4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    auto flush = [&]() {
+        // fp32 sums -> fp64 shared sums.  c0/c1: component 4g+2m, slots 8q+2t, +1; c2/c3: component 4g+2m+1
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int q = 0; q < NT; ++q) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int slot = 8 * q + 2 * t + (c & 1), comp = 4 * g + 2 * m + (c >> 1);
+                    if (slot < NA && comp < K) atomicAdd(&red[slot][comp], (double)acc[m][q][c]);
+                    acc[m][q][c] = 0.f;
+                }
+            }
+        // sum r: the four t-lanes of a g hold partial sums of the same four components
+        racc.x += __shfl_xor_sync(0xffffffffu, racc.x, 1); racc.x += __shfl_xor_sync(0xffffffffu, racc.x, 2);
+        racc.y += __shfl_xor_sync(0xffffffffu, racc.y, 1); racc.y += __shfl_xor_sync(0xffffffffu, racc.y, 2);
+        racc.z += __shfl_xor_sync(0xffffffffu, racc.z, 1); racc.z += __shfl_xor_sync(0xffffffffu, racc.z, 2);
+        racc.w += __shfl_xor_sync(0xffffffffu, racc.w, 1); racc.w += __shfl_xor_sync(0xffffffffu, racc.w, 2);
+        if (t == 0 && kin) {
+            atomicAdd(&red[NA][4 * g + 0], (double)racc.x);
+            atomicAdd(&red[NA][4 * g + 1], (double)racc.y);
+            atomicAdd(&red[NA][4 * g + 2], (double)racc.z);
+            atomicAdd(&red[NA][4 * g + 3], (double)racc.w);
+        }
+        racc = zero4;
+    };
+#pragma unroll 1
+    for (int64_t c = 0; c < ng; ++c) {
+        // refill the stage that group c-1 used (every lane is past it: __syncwarp; generic reads before the async-proxy write)
+        __syncwarp();
+        if (lane == 0 && c + SWM_NST - 1 < ng) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(c + SWM_NST - 1);
+        }
+        const float* st = ring + (c % SWM_NST) * SWM_STAGE;
+        sw_mbar_wait(&bars[wib][c % SWM_NST], (uint32_t)((c / SWM_NST) & 1));
+        const int64_t n0 = (gbeg + c) * 8;
+        const bool oka = kin && n0 + t < N, okb = kin && n0 + t + 4 < N;
+        const float4 r_a = oka ? *reinterpret_cast<const float4*>(st + SWM_XA + t * K + 4 * g) : zero4;
+        const float4 r_b = okb ? *reinterpret_cast<const float4*>(st + SWM_XA + (t + 4) * K + 4 * g) : zero4;
+        const float4 u_a = (oka && has_u) ? *reinterpret_cast<const float4*>(st + SWM_XA + 256 + t * K + 4 * g) : one4;
+        const float4 u_b = (okb && has_u) ? *reinterpret_cast<const float4*>(st + SWM_XA + 256 + (t + 4) * K + 4 * g) : one4;
+        racc.x += r_a.x + r_b.x; racc.y += r_a.y + r_b.y; racc.z += r_a.z + r_b.z; racc.w += r_a.w + r_b.w;
+        // A fragments: m-tile 0 = components (4g, 4g+1), m-tile 1 = (4g+2, 4g+3); columns = points t, t+4
+        uint32_t ah[2][4], al[2][4];
+        sw_split_tf32(r_a.x * u_a.x, ah[0][0], al[0][0]);
+        sw_split_tf32(r_a.y * u_a.y, ah[0][1], al[0][1]);
+        sw_split_tf32(r_b.x * u_b.x, ah[0][2], al[0][2]);
+        sw_split_tf32(r_b.y * u_b.y, ah[0][3], al[0][3]);
+        sw_split_tf32(r_a.z * u_a.z, ah[1][0], al[1][0]);
+        sw_split_tf32(r_a.w * u_a.w, ah[1][1], al[1][1]);
+        sw_split_tf32(r_b.z * u_b.z, ah[1][2], al[1][2]);
+        sw_split_tf32(r_b.w * u_b.w, ah[1][3], al[1][3]);
+        const float* xa = st + t * D;
+        const float* xb = xa + 4 * D;
+#pragma unroll
+        for (int q = 0; q < NT; ++q) {
+            uint32_t bh0, bl0, bh1, bl1;
+            sw_split_tf32(xa[oi[q]] * xa[oj[q]], bh0, bl0);
+            sw_split_tf32(xb[oi[q]] * xb[oj[q]], bh1, bl1);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                // the tensor core's fp32 accumulation truncates: only the 8-point partial goes through it, the
+                // running sums are added with round-to-nearest FADDs (5e-6 -> 1e-7 relative over a run)
+                float d[4];
+                sw_mma_tf32_zero(d, al[m], bh0, bh1);
+                sw_mma_tf32(d, ah[m], bl0, bl1);
+                sw_mma_tf32(d, ah[m], bh0, bh1);
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) acc[m][q][cc] += d[cc];
+            }
+        }
+        if ((c + 1) % SWM_FLUSH == 0) flush();
+    }
+    flush();
+    __syncthreads();
+    sw_store_stats<D>(red, K, u != nullptr, stats);
+    ng_tail_run<float>(tail, K, D, stats, gridDim.x);
+}
+
 // ---------------------------------------------------------------------------------------------------- E: e-step (+ next statistics)
 // Points are processed in groups of GP = 8 (four packed pairs): the eight score chains, the eight soft-max reductions and the
 // eight normalisations are independent, so the shuffle / MUFU latencies overlap instead of serialising per point.
@@ -446,8 +639,12 @@ sweep_estep_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
 #pragma unroll
     for (int e = 0; e < (STATS ? NA : 1); ++e) acc[e] = 0.f;
     float racc = 0.f;
-    for (int64_t run = gw; run * SW_RUN < N; run += nwarps) {
-        const int64_t r0 = run * SW_RUN, r1 = min(N, r0 + SW_RUN);
+    // every warp owns one contiguous, balanced range of 32-point batches (runs of SW_RUN points dealt round-robin left 18 % of
+    // the warps without work in the last wave at N = 10^6); inside it the fp32 statistics are flushed every SW_RUN points
+    const int64_t nbatch = (N + 31) / 32, per = (nbatch + nwarps - 1) / nwarps;
+    const int64_t wbeg = min(N, gw * per * 32), wend = min(N, wbeg + per * 32);
+    for (int64_t r0 = wbeg; r0 < wend; r0 += SW_RUN) {
+        const int64_t r1 = min(wend, r0 + SW_RUN);
         float pre[D];
         sw_load_x_clamped<D>(x, r0, (int)min((int64_t)32, r1 - r0), pre, lane);
         for (int64_t b0 = r0; b0 < r1; b0 += 32) {
@@ -548,6 +745,21 @@ template <int D>
 static int sw_launch_stats(int64_t N, int K, const float* x, const float* r, const float* u, double* stats, const NgTail& tail,
                            cudaStream_t st) {
     const bool aligned = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(u)) % 16 == 0);
+    if (D == 8 && aligned && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+        auto kern = sweep_stats_mma_kernel;
+        constexpr int ring_bytes = SW_WARPS * SWM_NST * SWM_STAGE * (int)sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0, sms = 148, occ = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SW_WARPS * 32, ring_bytes);
+        int64_t grid = (int64_t)sms * (occ < 1 ? 1 : occ);
+        const int64_t need = ((N + 7) / 8 + SW_WARPS - 1) / SW_WARPS;     // at least one group of 8 points per warp
+        if (grid > need) grid = need;
+        kern<<<(unsigned)(grid < 1 ? 1 : grid), SW_WARPS * 32, ring_bytes, st>>>(N, K, x, r, u, stats, tail);
+        return launch_status();
+    }
     if (aligned) {
         auto kern = sweep_stats_kernel<D, true>;
         constexpr int ring_bytes = SW_WARPS * 3 * 2 * 8 * 32 * (int)sizeof(float);
