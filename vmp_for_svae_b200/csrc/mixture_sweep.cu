@@ -423,9 +423,9 @@ sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
 // (m-tile mt, row g -> component 4g + 2mt, row g+8 -> component 4g + 2mt + 1).  B fragment = the feature (slot 8q + g) of the
 // points t, t+4, gathered from the staged x rows with per-lane constant offsets (the constants 1 and 0 sit behind the rows).
 // 36 MMAs + ~150 other instructions per 8 points (the FP32 lane <-> component kernel: 600).  What then binds is memory-level
-// parallelism: every warp owns a ring of SWM_NST bulk-copy (cp.async.bulk + mbarrier) stages, one stage = the contiguous x, r
-// and u rows of a group of 8 points, issued three groups ahead by lane 0; groups are dealt to the warps in contiguous,
-// balanced chunks (runs of 256 points left 18 % of the warps idle in the last wave at N = 10^6).
+// parallelism: every warp owns a ring of SWM_NST cp.async stages, one stage = the contiguous x, r and u rows of a group of 8
+// points, issued three groups ahead; groups are dealt to the warps in contiguous, balanced chunks (runs of 256 points left
+// 18 % of the warps idle in the last wave at N = 10^6).
 // d = a b (zero accumulator input)
 __device__ __forceinline__ void sw_mma_tf32_zero(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
@@ -442,51 +442,28 @@ __device__ __forceinline__ void sw_split_tf32(float v, uint32_t& hi, uint32_t& l
     lo = __float_as_uint(v - __uint_as_float(hi));        // the tensor core ignores the 13 low mantissa bits of lo
 }
 
-// per-warp ring of bulk-copy (TMA) stages: one stage = the x, r and u rows of one group of 8 points
+// per-warp ring of cp.async stages: one stage = the x, r and u rows of one group of 8 points
 constexpr int SWM_NST = 4;                      // stages per warp: 3 groups (6.9 KB) in flight behind the one being multiplied
 constexpr int SWM_XA = 128;                     // x area: 64 floats of rows | 1, 0 at [64], [65] and again at [96], [97]
-constexpr int SWM_STAGE = SWM_XA + 2 * 8 * 32;  // floats per stage: x area | r rows (8 x K) | u rows (8 x K)
-constexpr int SWM_FLUSH = 32;                   // groups between two flushes of the fp32 sums (256 points)
-
-__device__ __forceinline__ uint32_t sw_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sw_mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void sw_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sw_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void sw_mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "SW_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra SW_DONE_%=;\n\t"
-        "bra SW_WAIT_%=;\n\t"
-        "SW_DONE_%=:\n\t}" ::"r"(sw_smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void sw_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sw_smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(sw_smem_u32(bar))
-                 : "memory");
-}
+constexpr int SWM_RS = 36;                      // row stride of the staged r / u rows: 4 t-rows x 8 g-chunks hit 32 distinct bank quads
+constexpr int SWM_RA = 8 * SWM_RS;              // floats of one r (or u) area
+constexpr int SWM_STAGE = SWM_XA + 2 * SWM_RA;  // floats per stage: x area | r rows | u rows
+constexpr int SWM_FLUSH = 128;                  // groups between two flushes of the fp32 sums (1024 points; the fp64 shared-memory
+                                                // atomics of a flush cost as much as ~15 groups)
 
 __global__ void __launch_bounds__(SW_WARPS * 32, 2)
 sweep_stats_mma_kernel(int64_t N, int K, const float* __restrict__ x, const float* __restrict__ r, const float* __restrict__ u,
                        double* __restrict__ stats, const NgTail tail) {
     constexpr int D = 8, NA = sw_na(D), NT = 6;                     // 45 features in 6 n-tiles of 8 slots (3 spare = 0)
     __shared__ double red[NA + 1][32];
-    __shared__ __align__(8) uint64_t bars[SW_WARPS][SWM_NST];
     extern __shared__ __align__(128) float ring_raw[];               // [SW_WARPS][SWM_NST][SWM_STAGE]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     for (int e = threadIdx.x; e < (NA + 1) * 32; e += blockDim.x) (&red[0][0])[e] = 0.0;
     float* ring = ring_raw + (size_t)wib * SWM_NST * SWM_STAGE;
-    for (int e = lane; e < SWM_NST * SWM_STAGE; e += 32) {           // stale rows of a partial last group must be finite
+    for (int e = lane; e < SWM_NST * SWM_STAGE; e += 32) {           // the constants behind the x rows (never overwritten)
         const int o = e % SWM_STAGE;
         ring[e] = (o == 64 || o == 96) ? 1.f : 0.f;
     }
-    if (lane < SWM_NST) sw_mbar_init(&bars[wib][lane], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the zero fill above precedes the bulk copies
     __syncthreads();
     // slot 8q + g -> (i, j) of the augmented lower triangle (e = i (i + 1) / 2 + j); index 8 = the constant 1, spare slots = 0 * 0.
     // Offsets are relative to the row of point t (row t+4 is 32 floats further): the constants sit at [64 + d] and [96 + d].
@@ -505,19 +482,34 @@ sweep_stats_mma_kernel(int64_t N, int K, const float* __restrict__ x, const floa
     const int64_t per = (G + nwarps - 1) / nwarps, gbeg = min(G, gw * per), gend = min(G, gbeg + per);
     const int64_t ng = gend - gbeg;
     const bool kin = 4 * g < K, has_u = u != nullptr;
-    const uint32_t row_bytes = (uint32_t)K * 4u;
-    auto issue = [&](int64_t c) {                                    // lane 0: copies of group gbeg + c into stage c % NST
-        const int64_t n0 = (gbeg + c) * 8;
-        const uint32_t cnt = (uint32_t)min((int64_t)8, N - n0);
-        float* st = ring + (c % SWM_NST) * SWM_STAGE;
-        uint64_t* bar = &bars[wib][c % SWM_NST];
-        sw_mbar_expect_tx(bar, cnt * (32u + row_bytes * (has_u ? 2u : 1u)));
-        sw_bulk_g2s(st, x + n0 * D, cnt * 32u, bar);
-        sw_bulk_g2s(st + SWM_XA, r + n0 * K, cnt * row_bytes, bar);
-        if (has_u) sw_bulk_g2s(st + SWM_XA + 256, u + n0 * K, cnt * row_bytes, bar);
+    // copies of group gbeg + c into stage c % NST: 16-byte cp.async per lane (rows past N are zero-filled: zero weights, finite
+    // x), one commit group per stage.  (Bulk TMA copies of 256 B - 1 KB were request-bound: ~85 cycles each, 119 us per sweep.)
+    // this lane's (at most two) 16-byte chunks of the 8 x K block of r (and u): source / destination offsets are per-lane constants
+    int csrc[2], cdst[2], crow[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int e = lane + 32 * h, row = (4 * e) / K;
+        csrc[h] = 4 * e;
+        cdst[h] = SWM_XA + row * SWM_RS + (4 * e - row * K);
+        crow[h] = e < 2 * K ? row : 1 << 20;                         // no such chunk: never copied
+    }
+    auto issue = [&](int64_t c) {
+        if (c < ng) {
+            const int64_t n0 = (gbeg + c) * 8;
+            float* st = ring + (c % SWM_NST) * SWM_STAGE;
+            if (lane < 16) sw_cp_async16(st + 4 * lane, x + n0 * D + 4 * lane, n0 + (lane >> 1) < N);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (crow[h] < 8) {
+                    const bool ok = n0 + crow[h] < N;
+                    sw_cp_async16(st + cdst[h], ok ? r + n0 * K + csrc[h] : r, ok);
+                    if (has_u) sw_cp_async16(st + cdst[h] + SWM_RA, ok ? u + n0 * K + csrc[h] : u, ok);
+                }
+            }
+        }
+        sw_cp_commit();                                              // (an empty group keeps the wait_group arithmetic uniform)
     };
-    if (lane == 0)
-        for (int64_t c = 0; c < SWM_NST - 1 && c < ng; ++c) issue(c);
+    for (int64_t c = 0; c < SWM_NST - 1; ++c) issue(c);
     float acc[2][NT][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
@@ -555,20 +547,16 @@ sweep_stats_mma_kernel(int64_t N, int K, const float* __restrict__ x, const floa
     };
 #pragma unroll 1
     for (int64_t c = 0; c < ng; ++c) {
-        // refill the stage that group c-1 used (every lane is past it: __syncwarp; generic reads before the async-proxy write)
+        // refill the stage that group c-1 used (every lane is past it: __syncwarp), then wait for group c's copies
         __syncwarp();
-        if (lane == 0 && c + SWM_NST - 1 < ng) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            issue(c + SWM_NST - 1);
-        }
+        issue(c + SWM_NST - 1);
+        sw_cp_wait<SWM_NST - 1>();
+        __syncwarp();
         const float* st = ring + (c % SWM_NST) * SWM_STAGE;
-        sw_mbar_wait(&bars[wib][c % SWM_NST], (uint32_t)((c / SWM_NST) & 1));
-        const int64_t n0 = (gbeg + c) * 8;
-        const bool oka = kin && n0 + t < N, okb = kin && n0 + t + 4 < N;
-        const float4 r_a = oka ? *reinterpret_cast<const float4*>(st + SWM_XA + t * K + 4 * g) : zero4;
-        const float4 r_b = okb ? *reinterpret_cast<const float4*>(st + SWM_XA + (t + 4) * K + 4 * g) : zero4;
-        const float4 u_a = (oka && has_u) ? *reinterpret_cast<const float4*>(st + SWM_XA + 256 + t * K + 4 * g) : one4;
-        const float4 u_b = (okb && has_u) ? *reinterpret_cast<const float4*>(st + SWM_XA + 256 + (t + 4) * K + 4 * g) : one4;
+        const float4 r_a = kin ? *reinterpret_cast<const float4*>(st + SWM_XA + t * SWM_RS + 4 * g) : zero4;
+        const float4 r_b = kin ? *reinterpret_cast<const float4*>(st + SWM_XA + (t + 4) * SWM_RS + 4 * g) : zero4;
+        const float4 u_a = (kin && has_u) ? *reinterpret_cast<const float4*>(st + SWM_XA + SWM_RA + t * SWM_RS + 4 * g) : one4;
+        const float4 u_b = (kin && has_u) ? *reinterpret_cast<const float4*>(st + SWM_XA + SWM_RA + (t + 4) * SWM_RS + 4 * g) : one4;
         racc.x += r_a.x + r_b.x; racc.y += r_a.y + r_b.y; racc.z += r_a.z + r_b.z; racc.w += r_a.w + r_b.w;
         // A fragments: m-tile 0 = components (4g, 4g+1), m-tile 1 = (4g+2, 4g+3); columns = points t, t+4
         uint32_t ah[2][4], al[2][4];
@@ -599,9 +587,34 @@ sweep_stats_mma_kernel(int64_t N, int K, const float* __restrict__ x, const floa
                 for (int cc = 0; cc < 4; ++cc) acc[m][q][cc] += d[cc];
             }
         }
-        if ((c + 1) % SWM_FLUSH == 0) flush();
+        if ((c + 1) % SWM_FLUSH == 0 && c + 1 < ng) flush();
     }
-    flush();
+    // last flush without atomics: every warp dumps its fp32 sums into the (now idle) ring, 256 threads add the eight partials
+    // of each (slot, component) in double — the map (m, q, c, g, t) -> (slot, component) is one-to-one, so the add is plain
+    sw_cp_wait<0>();
+    __syncthreads();
+    float* dump = ring_raw;                                          // [SW_WARPS][2 * NT * 4][32]
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int q = 0; q < NT; ++q)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                dump[((wib * 2 * NT * 4) + (m * NT + q) * 4 + c) * 32 + lane] = acc[m][q][c];
+                acc[m][q][c] = 0.f;
+            }
+    flush();                                                         // (sum r; the accumulators are zero by now)
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 2 * NT * 4 * 32; idx += blockDim.x) {
+        const int reg = idx >> 5, l = idx & 31, m = reg / (NT * 4), q = (reg >> 2) % NT, c = reg & 3;
+        const int slot = 8 * q + 2 * (l & 3) + (c & 1), comp = 4 * (l >> 2) + 2 * m + (c >> 1);
+        if (slot < NA && comp < K) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < SW_WARPS; ++w) sum += (double)dump[((w * 2 * NT * 4) + reg) * 32 + l];
+            red[slot][comp] += sum;
+        }
+    }
     __syncthreads();
     sw_store_stats<D>(red, K, u != nullptr, stats);
     ng_tail_run<float>(tail, K, D, stats, gridDim.x);
