@@ -673,6 +673,42 @@ def test_tensor_core_suffstats_equals_fp32_kernel_and_fp64(N, r_is_log):
     assert torch.equal(S, S.transpose(1, 2))            # mirrored lower triangle: exactly symmetric
 
 
+@pytest.mark.parametrize('shape', [(64, 4, 32), (1000, 64, 32), (33000, 12, 32), (777, 8, 16), (20000, 32, 16)], ids=lambda s: 'N%dK%dD%d' % s)
+@pytest.mark.parametrize('mode', ['r', 'log_r', 'r_u'])
+def test_mma_statistics_d16_d32_vs_fp64(shape, mode):
+    """suffstats_mma.cu (mma.sync, split-tf32 operands; D in {16, 32}, K % 4 == 0) against an fp64 torch contraction and the
+    FP32 kernel (the same call with one extra zero-weight component: K + 1 is odd).  Per block, of the block's magnitude: 3e-6;
+    the second-moment block is exactly symmetric."""
+    from vmp_for_svae_b200 import core
+    N, K, D = shape
+    g = torch.Generator().manual_seed(N + K + D)
+    x = (torch.randn(N, D, generator=g, dtype=torch.float64) * 1.5 + torch.linspace(-4, 4, D, dtype=torch.float64)).to(DEV, torch.float32)
+    r64 = torch.softmax(2.0 * torch.randn(N, K, generator=g, dtype=torch.float64), dim=1)
+    is_log = mode == 'log_r'
+    rin = (torch.log(r64) if is_log else r64).to(DEV, torch.float32).contiguous()
+    u = (0.2 + 2.0 * torch.rand(N, K, generator=g, dtype=torch.float64)).to(DEV, torch.float32).contiguous() if mode == 'r_u' else None
+    got = core.suffstats(x, rin, r_is_log=is_log, u_nk=u).cpu()
+    pad = torch.full((N, 1), -1e30 if is_log else 0.0, dtype=torch.float32, device=DEV)
+    fp32 = core.suffstats(x, torch.cat([rin, pad], 1).contiguous(), r_is_log=is_log,
+                          u_nk=None if u is None else torch.cat([u, torch.ones_like(pad)], 1).contiguous()).cpu()[:K]
+    torch.cuda.synchronize()
+    rd = (torch.exp(rin.double()) if is_log else rin.double()).cpu()
+    xd = x.double().cpu()
+    w = rd * (u.double().cpu() if u is not None else 1.0)
+    ref = torch.zeros_like(got)
+    ref[:, 0] = rd.sum(0); ref[:, 1] = w.sum(0)
+    ref[:, 2:2 + D] = w.t() @ xd
+    ref[:, 2 + D:] = torch.einsum('nk,ni,nj->kij', w, xd, xd).reshape(K, D * D)
+    for name, out in (('mma', got), ('fp32', fp32)):
+        for lo, hi in ((0, 1), (1, 2), (2, 2 + D), (2 + D, 2 + D + D * D)):
+            scale = float(ref[:, lo:hi].abs().max())
+            err = float((out[:, lo:hi] - ref[:, lo:hi]).abs().max()) / scale
+            _report(test='mma statistics D16/D32', config=list(shape) + [mode], quantity='%s block %d:%d' % (name, lo, hi), err=err, rtol=3e-6)
+            assert err < 3e-6, (name, shape, mode, (lo, hi), err)
+    S = got[:, 2 + D:].reshape(K, D, D)
+    assert torch.equal(S, S.transpose(1, 2))
+
+
 @pytest.mark.parametrize('N', [1, 255, 4099, 70001])
 @pytest.mark.parametrize('K', [32, 12, 4])
 @pytest.mark.parametrize('weighted', [False, True], ids=['gmm', 'smm'])

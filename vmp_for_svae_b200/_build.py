@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libvmp_svae.so')
 HEADER = os.path.join(HERE, '..', 'include', 'vmp_svae.h')
 SOURCES = ['fast_d64.cu', 'fast_d32.cu', 'fast_d16.cu', 'fast_pack.cu',
-           'prepare.cu', 'local_step.cu', 'small_step.cu', 'local_step_bwd.cu', 'suffstats.cu', 'suffstats_tc.cu', 'mixtures.cu', 'mixture_sweep.cu', 'elbo_terms.cu', 'probe.cu']
+           'prepare.cu', 'local_step.cu', 'small_step.cu', 'local_step_bwd.cu', 'suffstats.cu', 'suffstats_tc.cu', 'suffstats_mma.cu', 'mixtures.cu', 'mixture_sweep.cu', 'elbo_terms.cu', 'probe.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-Xptxas', '-v', '-Wno-deprecated-gpu-targets']
 

@@ -310,6 +310,17 @@ int suffstats_tc_dispatch<float>(int64_t N, int K, int D, const float* x, const 
     return suffstats_tc(N, K, D, x, r, r_is_log, stats, tail, st);
 }
 
+// warp-level tensor-core contraction (suffstats_mma.cu): fp32, D in {16, 32}, K % 4 == 0, GMM or SMM weights
+int suffstats_mma(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u, double* stats,
+                  const NgTail& tail, cudaStream_t st);
+template <typename T>
+static int suffstats_mma_dispatch(int64_t, int, int, const T*, const T*, int, const T*, double*, const NgTail&, cudaStream_t) { return -100; }
+template <>
+int suffstats_mma_dispatch<float>(int64_t N, int K, int D, const float* x, const float* r, int r_is_log, const float* u_nk,
+                                  double* stats, const NgTail& tail, cudaStream_t st) {
+    return suffstats_mma(N, K, D, x, r, r_is_log, u_nk, stats, tail, st);
+}
+
 // fp32, D <= 8, K <= 32, plain responsibilities: the lane <-> component kernel of mixture_sweep.cu
 int sweep_stats_f32(int64_t N, int K, int D, const float* x, const float* r, const float* u, double* stats, const NgTail& tail,
                     cudaStream_t st);
@@ -331,6 +342,7 @@ int suffstats(int64_t N, int K, int D, const T* x, const T* r, int r_is_log, con
     if (!x || !r || !stats) return VMP_E_BADARG;
     if (int rc = sweep_stats_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, tail, (cudaStream_t)stream); rc != -100) return rc;
     if (int rc = suffstats_tc_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, tail, (cudaStream_t)stream); rc != -100) return rc;
+    if (int rc = suffstats_mma_dispatch(N, K, D, x, r, r_is_log, u_nk, stats, tail, (cudaStream_t)stream); rc != -100) return rc;
 #define VMP_SSM(DD) \
     case DD: return launch_suffstats_small<T, DD>(N, K, x, r, r_is_log, u_nk, stats, tail, (cudaStream_t)stream)
     switch (D) {
