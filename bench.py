@@ -416,14 +416,16 @@ def run_cuda(args):
     }
     # DRAM traffic of this kernel: STATIC figure from one ncu capture (profiles/), scaled to this launch's points — ncu cannot
     # run inside the timed job
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_traffic_local_step_fast64.json')) as f:
-            tr = json.load(f)
-        if (tr['K'], tr['D'], tr['S']) == (K, D, S):
-            roofline['traffic'] = tr['dram_bytes_per_point'] * n_per_gpu
-            roofline['traffic_source'] = 'static: ' + tr['source']
-    except (OSError, ValueError, KeyError):
-        pass
+    for name in ('r2_traffic_local_step_fast64.json', 'r1_traffic_local_step_fast64.json'):
+        try:
+            with open(os.path.join(ROOT, 'profiles', name)) as f:
+                tr = json.load(f)
+            if (tr['K'], tr['D'], tr['S']) == (K, D, S):
+                roofline['traffic'] = tr['dram_bytes_per_point'] * n_per_gpu
+                roofline['traffic_source'] = 'static: ' + tr['source']
+                break
+        except (OSError, ValueError, KeyError):
+            pass
     line = {
         'metric': METRIC, 'value': total_points / (ms_step * 1e-3), 'unit': 'points/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,
@@ -553,7 +555,7 @@ def run_cuda_sweep(args):
     fp32_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
     ach_gbs = by / (ms_step * 1e-3) / 1e9
     roofline = {
-        'kernel': 'one sweep = sweep_stats_kernel + sweep_prepare_kernel + sweep_estep_kernel (the two N-sized kernels are '
+        'kernel': 'one sweep = sweep_stats_mma_kernel (tensor cores) + sweep_prepare_kernel + sweep_estep_kernel (the two N-sized kernels are '
                   '>95 % of it; CUDA events around the whole sweep)',
         'bound': 'hbm', 'achieved': ach_gbs, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach_gbs / peaks['hbm_gbs'],
         'peak_source': 'hbm_gbs of MEASURED_PEAKS.json (%s)' % peak_src,

@@ -236,9 +236,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
     static_assert(bits_extract(GLMASK, GLMASK) == BS - 1, "GLMASK must have log2(BS) bits");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gl = (int)bits_extract((unsigned)lane, GLMASK);
-    const int lane_pair = lane & (int)(~GLMASK & 31u);        // this lane's pair bits: | bits_deposit(l, GLMASK) = lane of group-lane l
     const int grp = warp * GPW + (int)bits_extract((unsigned)lane, ~GLMASK & 31u);
-    auto group_bcast = [&](float v, int l) { return __shfl_sync(FULL, v, lane_pair | (int)bits_deposit((unsigned)l, GLMASK)); };
+    // value of group-lane l of this lane's pair: ONE shfl.idx whose segment mask (c[12:8]) keeps the pair bits of the lane id
+    // and takes the gl bits from the immediate source — PTX allows any 5-bit mask there, not only the 2^n - 1 "width" forms
+    auto group_bcast = [&](float v, int l) {
+        float out;
+        asm volatile("shfl.sync.idx.b32 %0, %1, %2, %3, 0xffffffff;"
+                     : "=f"(out)
+                     : "f"(v), "r"((int)bits_deposit((unsigned)l, GLMASK)), "r"((int)(((~GLMASK & 31u) << 8) | 0x1fu)));
+        return out;
+    };
     float* col = gsm + grp * GS;          // [2][D]
     float* vec = col + 2 * D;             // [D]
     float* ybf = vec + D;                 // [BS]
