@@ -744,7 +744,8 @@ def test_mma_small_statistics_vs_fp64(N, K, weighted):
 
 
 @pytest.mark.parametrize('dt', [torch.float64, torch.float32], ids=['f64', 'f32'])
-@pytest.mark.parametrize('shape', [(3000, 12, 64), (2000, 7, 64), (1500, 9, 32), (4000, 10, 6), (900, 40, 3), (50, 3, 2)],
+@pytest.mark.parametrize('shape', [(3000, 12, 64), (2000, 7, 64), (1500, 9, 32), (1500, 12, 32), (700, 8, 16), (4000, 12, 8), (4000, 10, 6),
+                                   (900, 40, 3), (50, 3, 2)],
                          ids=lambda s: 'N%dK%dD%d' % s)
 @pytest.mark.parametrize('only_alpha', [False, True], ids=['theta', 'alpha'])
 def test_fused_statistics_update_equals_two_launches(shape, dt, only_alpha):
