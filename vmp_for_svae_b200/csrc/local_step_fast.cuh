@@ -5,9 +5,10 @@
 // r < ROWS = 4, of the D x D system.  The lower triangle of P~ = P2_k + diag(p1_n) lives in registers
 // (A[r][c], c < (r+1)*BS; entries right of the diagonal are don't-care slots that are computed but never feed a
 // meaningful value), so the whole factorisation runs out of the register file:
-//   * right-looking Cholesky: at step j the pivot is broadcast with one shuffle, every lane scales its own entries
-//     of column j, publishes them to a 2 x D shared-memory column buffer, and updates its rows with the column read
-//     back as 128-bit broadcasts.  The update is issued as packed FFMA2 (PTX fma.rn.f32x2, sm_100): two FMAs per
+//   * right-looking factorisation in the square-root-free form P~ = Lu diag(d) Lu^T (L = Lu diag(sqrt d)): at step j
+//     the pivot d_j is broadcast with one shuffle, every lane publishes its RAW entries of column j to a 2 x D
+//     shared-memory column buffer, scales them by 1/d_j (its multipliers Lu[.][j]) and updates its rows with the raw
+//     column read back as 128-bit broadcasts.  The update is issued as packed FFMA2 (PTX fma.rn.f32x2, sm_100): two FMAs per
 //     instruction with the row's multiplier as broadcast scalar operand — measured 1.65x over scalar FFMA in THIS
 //     kernel because it halves the issue slots and the instruction footprint (the scalar build was instruction-fetch
 //     bound; in a pure register loop both forms reach the pipe's peak, tools/fp32_peak.py);
@@ -154,6 +155,11 @@ __device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, 
 __device__ __forceinline__ float lg2_approx(float x) {
     float r;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -364,39 +370,47 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 for (int cc = 0; cc < BS; ++cc) A[r][r * BS + cc] += (gl == cc) ? p1r : 0.f;
             });
 
-            // ---------------- phase 2: right-looking Cholesky with the two forward substitutions riding along
-            float q = 0.f, hl2 = 0.f;                                     // hl2 = sum_j log2(pivot_j)
+            // ---------------- phase 2: right-looking factorisation with the two forward substitutions riding along.
+            // Square-root-free form P~ = Lu diag(d) Lu^T (Lu unit lower, L = Lu diag(sqrt d)): the column is published RAW and the
+            // pivot-row values of the right-hand sides are broadcast RAW, so neither waits for the MUFU chain of the pivot —
+            // per column only the multipliers m = A[.][j] / d_j depend on it (SHFL -> RCP -> Newton -> FMUL), and that chain runs
+            // beside the store -> load round trip of the column instead of in front of it.  a = L^-1 g = z / sqrt d is formed per
+            // column for the samples; a . a1 = sum z z1 / d.
+            float q = 0.f, hl2 = 0.f;                                     // hl2 = sum_j log2(d_j)
             float yq[4], iq[4];
             static_for<0, D>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 constexpr int rj = j / BS, lj = j % BS;
                 const float piv = group_bcast(A[rj][j], lj);
-                float inv = rsqrt_approx(piv);                           // bare MUFU.RSQ (pivots are O(1): no denormals)
-                inv = inv * fmaf(-0.5f * piv * inv, inv, 1.5f);          // one Newton step: ~0.5 ulp
+                const float zj = group_bcast(g[rj], lj);
+                const float z1j = group_bcast(g1[rj], lj);
+                float* cw = col + (j & 1) * D;
+#pragma unroll
+                for (int r = rj; r < ROWS; ++r) cw[r * BS + gl] = A[r][j];
+                float rcp = rcp_approx(piv);                             // bare MUFU.RCP (pivots are O(1): no denormals)
+                rcp = fmaf(rcp, fmaf(-piv, rcp, 1.f), rcp);              // one Newton step: ~0.5 ulp
+                float rs = rsqrt_approx(piv);                            // 1 / L_jj, off the critical path
+                rs = rs * fmaf(-0.5f * piv * rs, rs, 1.5f);
                 hl2 += lg2_approx(piv);                                  // bare MUFU.LG2 (rel. error 2^-22; NaN flags a bad pivot)
-                const float yj = group_bcast(g[rj] * inv, lj);
-                const float y1j = group_bcast(g1[rj] * inv, lj);
-                q = fmaf(yj, y1j, q);
+                q = fmaf(zj * rcp, z1j, q);
                 // a_j and 1/L_jj go to shared memory (frees 8 registers); both are group-uniform, so four columns are
                 // batched into one 128-bit store each by lane 0 (6 fewer wavefronts per 4 columns than scalar stores)
-                yq[j & 3] = yj;
-                iq[j & 3] = inv;
+                yq[j & 3] = zj * rs;
+                iq[j & 3] = rs;
                 if constexpr ((j & 3) == 3) {
                     if (gl == 0) {
                         *reinterpret_cast<float4*>(ab + j - 3) = make_float4(yq[0], yq[1], yq[2], yq[3]);
                         *reinterpret_cast<float4*>(ib + j - 3) = make_float4(iq[0], iq[1], iq[2], iq[3]);
                     }
                 }
-                float* cw = col + (j & 1) * D;
 #pragma unroll
                 for (int r = rj; r < ROWS; ++r) {
-                    const float l = A[r][j] * inv;                       // owner's diagonal entry: piv * inv = L_jj
-                    A[r][j] = l;
-                    cw[r * BS + gl] = l;
-                    ffma2_bcast(g[r], g1[r], -l, yj, y1j);
+                    const float m = A[r][j] * rcp;                       // Lu[r][j] (the owner's diagonal entry becomes 1)
+                    A[r][j] = m;
+                    ffma2_bcast(g[r], g1[r], -m, zj, z1j);
                 }
                 __syncwarp();
-                // trailing update A[r][c] -= L[r][j] * L[c][j], c > j, as packed pairs (c0, c0+1)
+                // trailing update A[r][c] -= Lu[r][j] * A[c][j] (raw column), c > j, as packed pairs (c0, c0+1)
                 // the 128-bit broadcast reads are software-pipelined PF chunks ahead of their FFMA2s (ptxas otherwise
                 // recycles one 4-register buffer and exposes the shared-memory latency on every chunk)
                 constexpr int C4B = (j + 1) / 4, C4E = D / 4;
@@ -436,7 +450,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             float snum = 0.f, sden = 0.f;
             float x0[ROWS];
             for (int s = 0; s < S; ++s) {
-                float w[ROWS], y[ROWS], idg[ROWS];
+                float w[ROWS], y[ROWS];
                 if (p.noise != nullptr) {
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r)
@@ -453,8 +467,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
                     e2 = fmaf(w[r], w[r], e2);
-                    w[r] -= ab[r * BS + gl];
-                    idg[r] = ib[r * BS + gl];
+                    w[r] = (w[r] - ab[r * BS + gl]) * ib[r * BS + gl];  // L^T y = w  <=>  Lu^T y = w / sqrt d  (unit upper)
                     y[r] = 0.f;
                 }
                 // back substitution L^T y = w, block rows from the bottom
@@ -486,7 +499,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                         // rows 3..0 of the block: lane i finishes y_i, its in-block terms L[i][c] y_i wait in pd[c], c < i
                         float pd0 = 0.f, pd1 = 0.f, pd2 = 0.f;
                         {   // i = 3
-                            const float ym = (gl == 3) ? wv * idg[rb] : 0.f;
+                            const float ym = (gl == 3) ? wv : 0.f;
                             y[rb] = (gl == 3) ? ym : y[rb];
                             pd2 = A[rb][rb * 4 + 2] * ym;
                             pd1 = A[rb][rb * 4 + 1] * ym;
@@ -494,7 +507,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                         }
                         {   // i = 2: lane 2 needs pd2 of lane 3
                             const float t = group_bcast(pd2, 3);
-                            const float ym = (gl == 2) ? (wv - t) * idg[rb] : 0.f;
+                            const float ym = (gl == 2) ? (wv - t) : 0.f;
                             y[rb] = (gl == 2) ? ym : y[rb];
                             pd1 = fmaf(A[rb][rb * 4 + 1], ym, pd1);
                             pd0 = fmaf(A[rb][rb * 4 + 0], ym, pd0);
@@ -502,14 +515,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                         {   // i = 1: lane 1 needs pd1 of lanes 2 and 3 (lanes 0, 1 hold 0)
                             float t = pd1 + __shfl_xor_sync(FULL, pd1, 1 << HI);
                             t += __shfl_xor_sync(FULL, t, 1 << LO);
-                            const float ym = (gl == 1) ? (wv - t) * idg[rb] : 0.f;
+                            const float ym = (gl == 1) ? (wv - t) : 0.f;
                             y[rb] = (gl == 1) ? ym : y[rb];
                             pd0 = fmaf(A[rb][rb * 4 + 0], ym, pd0);
                         }
                         {   // i = 0
                             float t = pd0 + __shfl_xor_sync(FULL, pd0, 1 << HI);
                             t += __shfl_xor_sync(FULL, t, 1 << LO);
-                            if (gl == 0) y[rb] = (wv - t) * idg[rb];
+                            if (gl == 0) y[rb] = wv - t;
                         }
                         // every lane now owns its y of this block row: its terms for all earlier columns
                         if constexpr (rb > 0) {
@@ -544,8 +557,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                         __syncwarp();
     #pragma unroll
                         for (int i = BS - 1; i >= 0; --i) {
-                            const float t = tbf[i * TS + gl];               // L[rb*BS+i][rb*BS+gl]
-                            const float yi = group_bcast(w[rb] * idg[rb], i);
+                            const float t = tbf[i * TS + gl];               // Lu[rb*BS+i][rb*BS+gl]
+                            const float yi = group_bcast(w[rb], i);
                             y[rb] = (gl == i) ? yi : y[rb];
                             w[rb] = fmaf(-t, yi, w[rb]);
                         }
