@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             // per column only the multipliers m = A[.][j] / d_j depend on it (SHFL -> RCP -> Newton -> FMUL), and that chain runs
             // beside the store -> load round trip of the column instead of in front of it.  a = L^-1 g = z / sqrt d is formed per
             // column for the samples; a . a1 = sum z z1 / d.
-            float q = 0.f, hl2 = 0.f;                                     // hl2 = sum_j log2(d_j)
+            float q = 0.f, hl2 = 0.f;                                     // hl2 = sum_j log2(d_j), formed after the loop
             float yq[4], iq[4];
             static_for<0, D>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
@@ -389,14 +389,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 for (int r = rj; r < ROWS; ++r) cw[r * BS + gl] = A[r][j];
                 float rcp = rcp_approx(piv);                             // bare MUFU.RCP (pivots are O(1): no denormals)
                 rcp = fmaf(rcp, fmaf(-piv, rcp, 1.f), rcp);              // one Newton step: ~0.5 ulp
-                float rs = rsqrt_approx(piv);                            // 1 / L_jj, off the critical path
-                rs = rs * fmaf(-0.5f * piv * rs, rs, 1.5f);
-                hl2 += lg2_approx(piv);                                  // bare MUFU.LG2 (rel. error 2^-22; NaN flags a bad pivot)
                 q = fmaf(zj * rcp, z1j, q);
-                // a_j and 1/L_jj go to shared memory (frees 8 registers); both are group-uniform, so four columns are
-                // batched into one 128-bit store each by lane 0 (6 fewer wavefronts per 4 columns than scalar stores)
-                yq[j & 3] = zj * rs;
-                iq[j & 3] = rs;
+                // z_j and d_j go to shared memory (frees 8 registers); both are group-uniform, so four columns are batched
+                // into one 128-bit store each by lane 0.  1 / sqrt(d_j), a_j = z_j / sqrt(d_j) and log d_j are NOT formed here
+                // by all BS lanes redundantly: every lane does it for its own ROWS rows after the loop (8 instructions per
+                // column and lane saved)
+                yq[j & 3] = zj;
+                iq[j & 3] = piv;
                 if constexpr ((j & 3) == 3) {
                     if (gl == 0) {
                         *reinterpret_cast<float4*>(ab + j - 3) = make_float4(yq[0], yq[1], yq[2], yq[3]);
@@ -440,6 +439,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     }
                 });
             });
+            // own rows: 1 / L_ii = 1 / sqrt(d_i) (one Newton step: ~0.5 ulp), a_i = z_i / sqrt(d_i), sum of log2 d_i
+            float ar[ROWS], rsr[ROWS];
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const float d = ib[r * BS + gl];
+                float rs = rsqrt_approx(d);                              // bare MUFU.RSQ (pivots are O(1): no denormals)
+                rs = rs * fmaf(-0.5f * d * rs, rs, 1.5f);
+                rsr[r] = rs;
+                ar[r] = ab[r * BS + gl] * rs;
+                hl2 += lg2_approx(d);                                    // bare MUFU.LG2 (rel. error 2^-22; NaN flags a bad pivot)
+            }
+            hl2 = group_sum<GLMASK>(hl2);
             const float hld = 0.5f * (float)VMP_LOG_2 * hl2;           // sum_i log L_ii
             bad |= !(fabsf(hld) < CUDART_INF_F);                        // a non-positive pivot shows up as NaN / inf
             const float score = scl[0] - 0.5f * q + 0.5f * scl[1] - hld;
@@ -467,7 +478,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
 #pragma unroll
                 for (int r = 0; r < ROWS; ++r) {
                     e2 = fmaf(w[r], w[r], e2);
-                    w[r] = (w[r] - ab[r * BS + gl]) * ib[r * BS + gl];  // L^T y = w  <=>  Lu^T y = w / sqrt d  (unit upper)
+                    w[r] = (w[r] - ar[r]) * rsr[r];                     // L^T y = w  <=>  Lu^T y = w / sqrt d  (unit upper)
                     y[r] = 0.f;
                 }
                 // back substitution L^T y = w, block rows from the bottom
