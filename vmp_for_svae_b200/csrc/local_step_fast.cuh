@@ -376,8 +376,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             // per column only the multipliers m = A[.][j] / d_j depend on it (SHFL -> RCP -> Newton -> FMUL), and that chain runs
             // beside the store -> load round trip of the column instead of in front of it.  a = L^-1 g = z / sqrt d is formed per
             // column for the samples; a . a1 = sum z z1 / d.
-            float q = 0.f, hl2 = 0.f;                                     // hl2 = sum_j log2(d_j), formed after the loop
-            float yq[4], iq[4];
+            constexpr bool KEEP_Z = BS == 4;
+            float q = 0.f, hl2 = 0.f;                                     // a . a1 and sum_j log2(d_j)
+            float iq[4], yq[4];
             static_for<0, D>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 constexpr int rj = j / BS, lj = j % BS;
@@ -389,22 +390,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 for (int r = rj; r < ROWS; ++r) cw[r * BS + gl] = A[r][j];
                 float rcp = rcp_approx(piv);                             // bare MUFU.RCP (pivots are O(1): no denormals)
                 rcp = fmaf(rcp, fmaf(-piv, rcp, 1.f), rcp);              // one Newton step: ~0.5 ulp
-                q = fmaf(zj * rcp, z1j, q);
-                // z_j and d_j go to shared memory (frees 8 registers); both are group-uniform, so four columns are batched
-                // into one 128-bit store each by lane 0.  1 / sqrt(d_j), a_j = z_j / sqrt(d_j) and log d_j are NOT formed here
-                // by all BS lanes redundantly: every lane does it for its own ROWS rows after the loop (8 instructions per
-                // column and lane saved)
-                yq[j & 3] = zj;
+                // d_j (and z_j, see KEEP_Z) go to shared memory for the per-row epilogue below (group-uniform: four columns are
+                // batched into one 128-bit store by lane 0).  1 / sqrt(d_j), a_j and log d_j are NOT formed per column by all BS
+                // lanes redundantly: every lane does it for its own ROWS rows after the loop.
+                // KEEP_Z (BS = 4): z, z1 also stay in g, g1 of the row's owner (its own pivot-row update is masked out), so a . a1
+                // is per-row work too; at BS = 16 that keeps 8 more registers live through the loop and costs more in spills
+                // than it saves (measured 0.329 against 0.336), so z_j is staged and a . a1 accumulated per column there.
                 iq[j & 3] = piv;
+                if constexpr (!KEEP_Z) {
+                    q = fmaf(zj * rcp, z1j, q);
+                    yq[j & 3] = zj;
+                }
                 if constexpr ((j & 3) == 3) {
                     if (gl == 0) {
-                        *reinterpret_cast<float4*>(ab + j - 3) = make_float4(yq[0], yq[1], yq[2], yq[3]);
                         *reinterpret_cast<float4*>(ib + j - 3) = make_float4(iq[0], iq[1], iq[2], iq[3]);
+                        if constexpr (!KEEP_Z) *reinterpret_cast<float4*>(ab + j - 3) = make_float4(yq[0], yq[1], yq[2], yq[3]);
                     }
                 }
 #pragma unroll
                 for (int r = rj; r < ROWS; ++r) {
-                    const float m = A[r][j] * rcp;                       // Lu[r][j] (the owner's diagonal entry becomes 1)
+                    float m = A[r][j] * rcp;                             // Lu[r][j] (the owner's diagonal entry becomes 1)
+                    if (KEEP_Z && r == rj) m = (gl > lj) ? m : 0.f;      // rows <= j of this block row are finished: keep their z
                     A[r][j] = m;
                     ffma2_bcast(g[r], g1[r], -m, zj, z1j);
                 }
@@ -439,7 +445,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                     }
                 });
             });
-            // own rows: 1 / L_ii = 1 / sqrt(d_i) (one Newton step: ~0.5 ulp), a_i = z_i / sqrt(d_i), sum of log2 d_i
+            // own rows: 1 / L_ii = 1 / sqrt(d_i) (one Newton step: ~0.5 ulp), a_i = z_i / sqrt(d_i), a . a1, sum of log2 d_i
             float ar[ROWS], rsr[ROWS];
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
@@ -447,9 +453,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 float rs = rsqrt_approx(d);                              // bare MUFU.RSQ (pivots are O(1): no denormals)
                 rs = rs * fmaf(-0.5f * d * rs, rs, 1.5f);
                 rsr[r] = rs;
-                ar[r] = ab[r * BS + gl] * rs;
+                if constexpr (KEEP_Z) {
+                    ar[r] = g[r] * rs;
+                    q = fmaf(ar[r], g1[r] * rs, q);
+                } else {
+                    ar[r] = ab[r * BS + gl] * rs;
+                }
                 hl2 += lg2_approx(d);                                    // bare MUFU.LG2 (rel. error 2^-22; NaN flags a bad pivot)
             }
+            if constexpr (KEEP_Z) q = group_sum<GLMASK>(q);
             hl2 = group_sum<GLMASK>(hl2);
             const float hld = 0.5f * (float)VMP_LOG_2 * hl2;           // sum_i log L_ii
             bad |= !(fabsf(hld) < CUDART_INF_F);                        // a non-positive pivot shows up as NaN / inf
