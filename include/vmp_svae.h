@@ -192,7 +192,12 @@ int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, int64_t po
  * (smm.py:25-50,167-196) in additive form: stats[k] += [sum r, sum w, sum w x, sum w x x^T], w = r (GMM) or
  * r*u (SMM, u_nk != NULL).  x[N,D]; r[N,K] = responsibilities, or their logs when r_is_log != 0
  * (the SVAE path feeds log_r straight in: experiments.py:258-259 does tf.exp).  stats[K, vmp_stats_len(D)]
- * is double and ACCUMULATED into (zero it first; all-reduce it across ranks before the update).      */
+ * is double and ACCUMULATED into (zero it first; all-reduce it across ranks before the update).
+ * Which kernel runs is a function of the arguments alone.  fp32: D = 64 with even K and GMM weights -> tcgen05 contraction
+ * (suffstats_tc.cu); D in {16, 32} with K % 4 == 0 -> warp-level mma.sync (suffstats_mma.cu); D <= 8, K <= 32, plain r ->
+ * the sweep statistics of mixture_sweep.cu (mma.sync at D = 8, K % 4 == 0); everything else and fp64 -> FP32 / FP64 FMA
+ * kernels (suffstats.cu).  The tensor-core paths feed split-tf32 operands (hi*hi + lo*hi + hi*lo) and agree with an fp64
+ * contraction to <= 3e-6 of each block's magnitude; the second-moment block is exactly symmetric on every path.        */
 int vmp_suffstats_f32(int64_t N, int K, int D, const float* x, const float* r, int r_is_log,
                       const float* u_nk, double* stats, void* stream);
 int vmp_suffstats_f64(int64_t N, int K, int D, const double* x, const double* r, int r_is_log,
