@@ -328,6 +328,34 @@ def test_fused_step_vs_oracle(shape, dt):
             check('step theta_new.' + n, t, r, rt, float(r.abs().max()), **ctx)
 
 
+def test_inkernel_noise_stream_is_standard_normal_and_uniform():
+    """The in-kernel noise (Philox4x32-10 + Box-Muller on the special-function unit, common.cuh) as vmp_fill_noise writes it:
+    4.2 M normals have the moments and the CDF of N(0,1) (sampling error of the max CDF gap at this size: ~7e-4), are
+    uncorrelated between neighbouring dimensions / samples, and the Gumbel uniforms are uniform on (0,1)."""
+    from vmp_for_svae_b200 import core
+    noise, u = core.fill_noise(8192, 16, 8, 4, seed=12345, dtype=torch.float32, device=DEV)
+    torch.cuda.synchronize()
+    v = noise.double().flatten().cpu()
+    n = v.numel()
+    assert torch.isfinite(v).all()
+    m, var = float(v.mean()), float(v.var())
+    skew = float(((v - m) ** 3).mean() / var ** 1.5)
+    kurt = float(((v - m) ** 4).mean() / var ** 2)
+    assert abs(m) < 2.5e-3 and abs(var - 1) < 4e-3 and abs(skew) < 6e-3 and abs(kurt - 3) < 2e-2, (m, var, skew, kurt)
+    xs = torch.linspace(-4, 4, 81, dtype=torch.float64)
+    emp = torch.tensor([float((v <= x).double().mean()) for x in xs])
+    cdf = 0.5 * (1 + torch.erf(xs / 2 ** 0.5))
+    assert float((emp - cdf).abs().max()) < 2.5e-3
+    assert float(v.abs().max()) > 4.5                                   # the tails are there (P(|x| > 4.5) n = 28)
+    w = noise.double().cpu()
+    for a, b in ((w[..., 0::2, :], w[..., 1::2, :]), (w[..., 0::2], w[..., 1::2])):        # pairs out of one Box-Muller / one Philox block
+        assert abs(float((a * b).mean())) < 3e-3
+    uu = u.double().flatten().cpu()
+    assert float(uu.min()) > 0 and float(uu.max()) < 1
+    assert abs(float(uu.mean()) - 0.5) < 3e-3 and abs(float(uu.var()) - 1 / 12) < 1.5e-3
+    _report(test='noise stream', quantity='moments [mean, var, skew, kurt-3]', err=max(abs(m), abs(var - 1), abs(skew), abs(kurt - 3)), n=n)
+
+
 def test_inkernel_noise_equals_injected_noise():
     from vmp_for_svae_b200 import core
     from vmp_for_svae_b200.step import SVAEStep
