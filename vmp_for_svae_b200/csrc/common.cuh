@@ -97,10 +97,16 @@ struct Philox {
 // (k + 1/2 needs 24 significant bits), so the result is never 0 or 1 (safe for log / Box-Muller / Gumbel)
 __host__ __device__ __forceinline__ float u32_to_unit(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
-// four standard normals for (pair, sample s, dims 4q..4q+3) — the definition of the in-kernel noise stream
-__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t pair, uint32_t s, uint32_t q) {
+// the 9 low bits of three Philox words that u32_to_unit leaves unused -> one more uniform (27 bits, the top 23 used)
+__host__ __device__ __forceinline__ float philox_spare_uniform(uint4 r) {
+    return u32_to_unit(((r.x & 0x1ffu) << 23) | ((r.y & 0x1ffu) << 14) | ((r.z & 0x1ffu) << 5));
+}
+// four standard normals for (pair, sample s, dims 4q..4q+3) — the definition of the in-kernel noise stream; *spare = the
+// uniform made of the block's unused low bits (the Gumbel uniform of the pair when s = q = 0, see philox_uniform_pair)
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t pair, uint32_t s, uint32_t q, float* spare = nullptr) {
     const uint4 r = Philox::gen(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), s, q),
                                 make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    if (spare != nullptr) *spare = philox_spare_uniform(r);
     const float u0 = u32_to_unit(r.x), u1 = u32_to_unit(r.y), u2 = u32_to_unit(r.z), u3 = u32_to_unit(r.w);
     // Box-Muller on the special-function unit: radius sqrt(-2 ln u) from MUFU.LG2 + MUFU.SQRT, direction from MUFU.SIN / MUFU.COS
     // at theta = 2 pi u - pi in (-pi, pi) (absolute error ~5e-7): 12 instructions per pair of normals instead of ~60 for
@@ -123,11 +129,13 @@ __device__ __forceinline__ float philox_normal1(uint64_t seed, uint64_t pair, ui
     const uint32_t c = d & 3u;
     return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
 }
-// the uniform behind the Gumbel-max categorical draw of pair (n,k) — the in-kernel definition of u[n,k]
+// the uniform behind the Gumbel-max categorical draw of pair (n,k) — the in-kernel definition of u[n,k]: the spare low bits of
+// the Philox block that also yields the pair's first four normals (s = 0, q = 0), so a kernel that draws those normals gets the
+// uniform without a second Philox call
 __device__ __forceinline__ float philox_uniform_pair(uint64_t seed, uint64_t pair) {
-    const uint4 r = Philox::gen(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), 0x5eedu, 0xca7u),
-                                make_uint2((uint32_t)seed ^ 0xA511E9B3u, (uint32_t)(seed >> 32)));
-    return u32_to_unit(r.x);
+    const uint4 r = Philox::gen(make_uint4((uint32_t)pair, (uint32_t)(pair >> 32), 0u, 0u),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    return philox_spare_uniform(r);
 }
 // Gumbel(0,1) from a uniform: tf.multinomial's GPU kernel draws z = argmax_k(logit_k - log(-log(u_k)))
 template <typename T> __device__ __forceinline__ T gumbel_from_uniform(T u) { return -t_log(-t_log(u)); }

@@ -472,7 +472,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
             const uint64_t gpair = pair + p.pair_offset;                      // key of the in-kernel noise stream
             float snum = 0.f, sden = 0.f;
             float x0[ROWS];
+            float u_pair = 0.f;                                           // Gumbel uniform of the pair (spare bits of its first Philox block)
             for (int s = 0; s < S; ++s) {
+                float u_spare = 0.f;
                 float w[ROWS], y[ROWS];
                 if (p.noise != nullptr) {
 #pragma unroll
@@ -480,8 +482,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                         w[r] = (r * BS + gl < Dr) ? p.noise[(pair * Dr + r * BS + gl) * (uint64_t)S + s] : 0.f;
                 } else {
                     __syncwarp();
-                    for (int qd = gl; qd < D / 4; qd += BS)
-                        reinterpret_cast<float4*>(vec)[qd] = philox_normal4(p.seed, gpair, (uint32_t)s, (uint32_t)qd);
+                    for (int qd = gl; qd < D / 4; qd += BS) {
+                        float sp;
+                        reinterpret_cast<float4*>(vec)[qd] = philox_normal4(p.seed, gpair, (uint32_t)s, (uint32_t)qd, &sp);
+                        if (qd < BS) u_spare = sp;
+                    }
+                    if (s == 0) u_pair = group_bcast(u_spare, 0);        // block (s = 0, q = 0) is group-lane 0's first call
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < ROWS; ++r) w[r] = (r * BS + gl < Dr) ? vec[r * BS + gl] : 0.f;
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) local_step_fast_kernel(const
                 kst[3 * k + 2] = sden / (float)S;
             }
             // online Gumbel-max draw of z_n (tf.multinomial GPU algorithm): keep the running arg-max and its sample
-            const float u = p.gum_u != nullptr ? p.gum_u[pair] : philox_uniform_pair(p.seed, gpair);
+            const float u = p.gum_u != nullptr ? p.gum_u[pair] : (p.noise != nullptr ? philox_uniform_pair(p.seed, gpair) : u_pair);
             const float cand = score + gumbel_from_uniform<float>(u);
             if (cand > best) {
                 best = cand;
