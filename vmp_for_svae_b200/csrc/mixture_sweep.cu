@@ -330,7 +330,7 @@ sweep_stats_kernel(int64_t N, int K, const float* __restrict__ x, const float* _
     constexpr int NA = sw_na(D), GP = 8, NST = 3;
     __shared__ double red[NA + 1][32];
     __shared__ __align__(16) float xsm[SW_WARPS][32 * D];
-    extern __shared__ __align__(16) float ring_raw[];                // ASYNC: [SW_WARPS][NST][2][GP * 32]
+    extern __shared__ __align__(128) float ring_raw[];                // ASYNC: [SW_WARPS][NST][2][GP * 32]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float* ring_w = ring_raw + (size_t)wib * NST * 2 * GP * 32;
     for (int t = threadIdx.x; t < (NA + 1) * 32; t += blockDim.x) (&red[0][0])[t] = 0.0;
