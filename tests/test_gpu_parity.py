@@ -58,7 +58,7 @@ TOL = {torch.float32: 1e-5, torch.float64: 1e-10}
 def rtol_for(dt, D, base=None):
     if dt == torch.float64:
         return 1e-9
-    return 1e-5 if D <= 8 else (5e-5 if D <= 16 else 2e-4)
+    return 1e-5 if D <= 8 else (2e-5 if D <= 16 else 5e-5)     # measured worst case: 6.7e-6 / 5.0e-6 / 1.7e-5
 
 
 def logr_atol(dt, D):
