@@ -181,7 +181,11 @@ int vmp_svae_local_step_bwd_f64(int64_t N, int K, int D, int S, const double* et
                                 void* stream);
 
 /* The noise the in-kernel generator uses for a given seed, written in the reference layout
- * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N,K] (either may be NULL).      */
+ * (tests: injected-noise path == in-kernel path).  noise[N,K,D,S], u[N,K] (either may be NULL).
+ * Definition of the stream: block(pair, s, q) = Philox4x32-10(counter = (pair_lo, pair_hi, s, q), key = seed) with
+ * pair = (point_offset + n) * K + k; the four normals of dims 4q..4q+3 of sample s are two Box-Muller pairs of the
+ * words' top 23 bits (bin centres (j + 1/2) / 2^23; radius and direction evaluated with lg2 / sqrt / sin / cos .approx);
+ * u[n,k] is built from the 9 unused low bits of three words of block(pair, 0, 0).                                 */
 int vmp_fill_noise_f32(int64_t N, int K, int D, int S, uint64_t seed, int64_t point_offset, float* noise, float* u,
                        void* stream);
 int vmp_fill_noise_f64(int64_t N, int K, int D, int S, uint64_t seed, int64_t point_offset, double* noise, double* u,
