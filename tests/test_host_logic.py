@@ -73,6 +73,60 @@ def test_uniform_mapping_never_hits_0_or_1(tmp_path):
     assert np.isfinite(-np.log(-np.log(np.float32(vals[4])))) and np.isfinite(-np.log(-np.log(np.float32(vals[0]))))
 
 
+def test_engine_lane_numbering_and_spare_uniform(tmp_path):
+    """Host compile of the engines' lane numbering (local_step_fast.cuh: FastGeom::GLMASK, bits_deposit / bits_extract) and of
+    the spare-bit Gumbel uniform (common.cuh).  The measured shared-memory rule (profiles/r2_smem_lane_bits.md) wants neither
+    the group-lane bits nor the pair bits to contain BOTH b0 and b1; the numbering must be a bijection of the 32 lanes; the
+    source lane of a group broadcast keeps the pair bits; the spare uniform lies strictly inside (0,1)."""
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    if not os.path.exists(nvcc):
+        pytest.skip('nvcc not available')
+    csrc = os.path.join(ROOT, 'vmp_for_svae_b200', 'csrc')
+    src = tmp_path / 'g.cu'
+    src.write_text(r"""
+#include <cstdio>
+#define VMP_FAST_IMPL
+#include "%s/local_step_fast.cuh"
+using namespace vmp;
+template <int D, int BS> int check() {
+    constexpr unsigned M = FastGeom<D, BS>::GLMASK, P = ~M & 31u;
+    int bad = 0;
+    bad += __builtin_popcount(M) != __builtin_ctz((unsigned)BS);
+    bad += (M & 3u) == 3u;                       // gl on both b0 and b1: 4-wavefront row reads
+    bad += (P & 3u) == 3u;                       // pair on both b0 and b1: 4-wavefront column broadcasts
+    bool seen[32] = {};
+    for (unsigned lane = 0; lane < 32; ++lane) {
+        const unsigned gl = bits_extract(lane, M), pr = bits_extract(lane, P);
+        bad += gl >= (unsigned)BS || pr >= 32u / BS;
+        const unsigned id = pr * BS + gl;
+        bad += seen[id];
+        seen[id] = true;
+        bad += (bits_deposit(gl, M) | bits_deposit(pr, P)) != lane;
+        for (unsigned l = 0; l < (unsigned)BS; ++l) {                      // source lane of group_bcast(v, l)
+            const unsigned src = (lane & P) | bits_deposit(l, M);
+            bad += bits_extract(src, P) != pr || bits_extract(src, M) != l;
+        }
+    }
+    return bad;
+}
+int main() {
+    printf("%%d %%d %%d %%d\n", check<64, 16>(), check<32, 8>(), check<32, 4>(), check<16, 4>());
+    const uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    const uint4 mix = make_uint4(0x1ffu, 0u, 0u, 0u);
+    printf("%%.17g %%.17g %%.17g\n", (double)philox_spare_uniform(lo), (double)philox_spare_uniform(hi), (double)philox_spare_uniform(mix));
+    return 0;
+}
+""" % csrc)
+    exe = tmp_path / 'g'
+    subprocess.check_call([nvcc, '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', str(exe), str(src)],
+                          stderr=subprocess.DEVNULL)
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert [int(v) for v in out[:4]] == [0, 0, 0, 0]
+    u = [float(v) for v in out[4:]]
+    assert u[0] == 0.5 / 8388608 and u[1] == (8388607 + 0.5) / 8388608 and 0.0 < u[0] < u[2] < u[1] < 1.0
+    assert u[2] == (0x1ff * 2 ** 14 + 0.5) / 8388608           # the 9 low bits of word x are the top bits of the uniform
+
+
 def test_shard_range_partitions():
     from vmp_for_svae_b200.dist import shard_range
     for n in (0, 1, 7, 100, 1 << 20):
